@@ -1,0 +1,176 @@
+/* gsb200.h -- C ABI of libgsb200.so, the B200-native (sm_100a) replacement for the native code
+ * under InstantSplat's training hot path.  Plain pointers and sizes only; no torch types.
+ * All pointers are DEVICE pointers unless the name ends in _host.  All tensors fp32, contiguous.
+ * Every entry point enqueues work on `stream` and returns 0 on success or a negative error code
+ * (GSB_ERR_*); none of them throws.  Buffers are caller-owned (the Python layer uses torch
+ * allocations), sized with the gsb_*_bytes() helpers.
+ *
+ * What each entry point replaces in the reference (files under /root/reference):
+ *
+ *   gsb_preprocess + gsb_render   ->  diff_gaussian_rasterization._C.rasterize_gaussians, called by
+ *                                     GaussianRasterizer.forward at gaussian_renderer/__init__.py:126-135
+ *                                     (settings built at :60-76).  With `pose` set they also absorb
+ *                                     the pose pre-transform (:81-89), the activations
+ *                                     (scene/gaussian_model.py:101-121) and the feature cat (:113-117).
+ *   gsb_backward                  ->  _C.rasterize_gaussians_backward (autograd of the call above,
+ *                                     triggered by train.py:177) plus the ATen backward of
+ *                                     utils/pose_utils.py:57-104 (quad2rotation / quadmultiply) that
+ *                                     yields gaussians.P.grad.
+ *   gsb_mark_visible              ->  _C.mark_visible (GaussianRasterizer.markVisible).
+ *   gsb_ssim_forward/backward     ->  fused_ssim.fused_ssim, train.py:39-43,172-173
+ *                                     (fallback utils/loss_utils.py:55-85).
+ *   gsb_loss_forward/backward     ->  train.py:171-176: l1_loss (utils/loss_utils.py:39-40) + SSIM +
+ *                                     the (1-l)*L1 + l*(1-ssim) combine, fused.
+ *   gsb_adam_step                 ->  scene/per_point_adam.py:34-98 (PerPointAdam.step) for up to
+ *                                     GSB_ADAM_MAX_TENSORS tensors in one launch.
+ *                                     GsbAdamTensor.grad_scale folds in the x 1/G after the NCCL sum of
+ *                                     per-Gaussian gradients.
+ */
+#ifndef GSB200_H_
+#define GSB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GSB_API __attribute__((visibility("default")))
+#else
+#define GSB_API
+#endif
+
+typedef void* gsb_stream_t; /* cudaStream_t */
+
+#define GSB_OK 0
+#define GSB_ERR_INVALID (-1)  /* bad argument (shape / NULL / alignment) */
+#define GSB_ERR_CUDA (-2)     /* a CUDA call failed; see gsb_last_error() */
+#define GSB_ERR_CAPACITY (-3) /* caller-provided buffer too small */
+
+#define GSB_ADAM_MAX_TENSORS 8
+
+/* Rasterizer settings: GaussianRasterizationSettings of the reference
+ * (gaussian_renderer/__init__.py:60-76).  viewmatrix/projmatrix are stored transposed
+ * (row-vector convention, scene/cameras.py:54-56): p_view = [p,1] @ viewmatrix. */
+typedef struct GsbCamera {
+  int32_t width, height;
+  float tanfovx, tanfovy;
+  float scale_modifier;
+  int32_t sh_degree;       /* active degree D (0..3) */
+  int32_t sh_coeffs;       /* M: coefficients stored per Gaussian (1, 4, 9 or 16) */
+  int32_t exact_cull;      /* 1: lossless alpha<1/255 tile culling (default); 0: reference rect only */
+  const float* bg;         /* [3] */
+  const float* viewmatrix; /* [16] */
+  const float* projmatrix; /* [16] */
+  const float* campos;     /* [3] */
+} GsbCamera;
+
+/* Gaussian inputs.  Exactly one of (sh_dc[,sh_rest]) / colors_precomp and one of
+ * (scales+rotations) / cov3D_precomp must be given. */
+typedef struct GsbGaussians {
+  int32_t P;
+  int32_t sh_packed;           /* 1: sh_dc points at a packed [P,M,3] tensor (B2 boundary);
+                                  0: sh_dc [P,3] and sh_rest [P,M-1,3] (the model's own tensors) */
+  int32_t raw_params;          /* 1: scales are log-scales and opacities logits (activations fused) */
+  int32_t reserved;
+  const float* means3D;        /* [P,3] */
+  const float* scales;         /* [P,3] */
+  const float* rotations;      /* [P,4] raw quaternions, real first, never normalised */
+  const float* opacities;      /* [P] */
+  const float* sh_dc;
+  const float* sh_rest;
+  const float* colors_precomp; /* [P,3] or NULL */
+  const float* cov3D_precomp;  /* [P,6] or NULL */
+  const float* pose;           /* [7] = qw,qx,qy,qz,tx,ty,tz or NULL: fused InstantSplat pre-transform */
+} GsbGaussians;
+
+/* Gradients w.r.t. the tensors of GsbGaussians (dense, every row written).  NULL = not wanted. */
+typedef struct GsbGrads {
+  float* dL_dmeans3D;   /* [P,3] */
+  float* dL_dmeans2D;   /* [P,3]  d/d(ndc x,y), z = 0 */
+  float* dL_dscales;    /* [P,3] */
+  float* dL_drotations; /* [P,4] */
+  float* dL_dopacities; /* [P] */
+  float* dL_dsh_dc;     /* layout mirrors sh_dc / sh_rest */
+  float* dL_dsh_rest;
+  float* dL_dcolors;    /* [P,3] (colors_precomp) */
+  float* dL_dcov3D;     /* [P,6] (cov3D_precomp) */
+  float* dL_dpose;      /* [7] (pose) */
+} GsbGrads;
+
+GSB_API size_t gsb_geom_bytes(int32_t P);
+GSB_API size_t gsb_binning_bytes(int64_t R, int32_t width, int32_t height);
+GSB_API size_t gsb_image_bytes(int32_t width, int32_t height);
+
+/* Phase 1: per-Gaussian projection (+ fused pose / activations / SH->RGB), depth sort and tile
+ * counting.  Writes radii [P] (int32) and the number of (Gaussian, tile) instances R to
+ * *num_rendered_host (pinned host memory, valid after the stream reaches this point). */
+GSB_API int gsb_preprocess(const GsbCamera* cam, const GsbGaussians* g, void* geom, size_t geom_bytes,
+                   int32_t* radii, uint32_t* num_rendered_host, gsb_stream_t stream);
+
+/* Phase 2: binning (duplicate, tile sort, ranges, slab gather) and the per-tile blend.
+ * R must be the value produced by gsb_preprocess.  out_color [3,H,W]. */
+GSB_API int gsb_render(const GsbCamera* cam, int32_t P, void* geom, void* binning, size_t binning_bytes,
+               int64_t R, void* image, float* out_color, gsb_stream_t stream);
+
+/* Backward of gsb_preprocess + gsb_render.  dL_dout [3,H,W]. */
+GSB_API int gsb_backward(const GsbCamera* cam, const GsbGaussians* g, void* geom, void* binning, int64_t R,
+                 void* image, const float* dL_dout, const GsbGrads* grads, gsb_stream_t stream);
+
+GSB_API int gsb_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, gsb_stream_t stream);
+
+/* SSIM (11x11, sigma 1.5, zero 'same' padding, C1=1e-4, C2=9e-4), images [B,C,H,W].
+ * forward: sums2[1] += sum of the SSIM map (double[2]; caller zeroes it and divides by B*C*H*W);
+ * if maps != NULL ([3,B,C,H,W]) the three partial-derivative maps are stored for backward. */
+GSB_API int gsb_ssim_forward(int32_t BC, int32_t H, int32_t W, const float* img1, const float* img2,
+                     double* sums2, float* maps, gsb_stream_t stream);
+/* dL_dimg1 = scale_host * d(sum ssim)/d(img1) * (*dL_dmean_scale if not NULL) */
+GSB_API int gsb_ssim_backward(int32_t BC, int32_t H, int32_t W, const float* img1, const float* img2,
+                      const float* maps, float scale_host, const float* dL_dmean_scale,
+                      float* dL_dimg1, gsb_stream_t stream);
+
+/* Fused training loss of train.py:171-176 on one image [C,H,W]:
+ * sums[0] += sum|img-gt|, sums[1] += sum ssim_map (double[2], caller zeroes it). */
+GSB_API int gsb_loss_forward(int32_t C, int32_t H, int32_t W, const float* img, const float* gt,
+                     double* sums, float* maps, gsb_stream_t stream);
+/* dL_dimg = (1-lambda)/N * sign(img-gt) - lambda/N * d(sum ssim)/d(img), N = C*H*W */
+GSB_API int gsb_loss_backward(int32_t C, int32_t H, int32_t W, const float* img, const float* gt,
+                      const float* maps, float lambda_dssim, float* dL_dimg, gsb_stream_t stream);
+
+/* Per-point Adam (scene/per_point_adam.py:34-98), n tensors in one launch. */
+typedef struct GsbAdamTensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  const float* per_point_lr; /* [rows] or NULL */
+  int64_t numel;
+  int32_t row_len;           /* numel / rows (elements sharing one per_point_lr entry) */
+  float grad_scale;          /* gradient is multiplied by this first (1/G after an NCCL sum) */
+  double step_size;          /* lr * sqrt(1-b2^t) / (1-b1^t), computed on the host in double */
+  double beta1, beta2, eps, weight_decay;
+} GsbAdamTensor;
+/* flags: [n] uint32 scratch (device); gate g.norm()>0 per tensor is evaluated on the device. */
+GSB_API int gsb_adam_step(int32_t n, const GsbAdamTensor* tensors_host, uint32_t* flags, gsb_stream_t stream);
+
+/* Optional instrumentation (bench.py): per-kernel CUDA-event timing on the launching stream and a
+ * count of this library's own kernel launches (cub launches are not counted). */
+enum {
+  GSB_K_PREPROCESS = 0, GSB_K_SORT_DEPTH, GSB_K_SCAN, GSB_K_DUPLICATE, GSB_K_SORT_TILE, GSB_K_GATHER,
+  GSB_K_BLEND_FWD, GSB_K_BLEND_BWD, GSB_K_PREPROCESS_BWD, GSB_K_LOSS_FWD, GSB_K_LOSS_BWD, GSB_K_ADAM,
+  GSB_K_COUNT
+};
+GSB_API void gsb_profile_enable(int on);
+GSB_API int gsb_profile_collect(double* ms_sum, int64_t* count, int n_ids);
+GSB_API uint64_t gsb_launch_count(void);
+
+GSB_API const char* gsb_last_error(void);
+GSB_API int gsb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSB200_H_ */

@@ -1,0 +1,165 @@
+// Fused per-point Adam for sm_100a: all parameter tensors of the Gaussian model (and the pose
+// table) in ONE launch, no host synchronisation.
+//
+// Semantics are those of /root/reference/scene/per_point_adam.py:34-98:
+//   * whole-tensor gate  mask = grad.norm() > 0  (:66-67): moments are updated only when the
+//     gradient tensor is not identically zero; evaluated on the device by k_adam_gate
+//   * old-style bias correction folded into step_size = lr*sqrt(1-b2^t)/(1-b1^t) (:76-81),
+//     denom = sqrt(v) + eps (eps NOT divided by sqrt(bc2))
+//   * optional per-row learning-rate multiplier per_point_lr [rows,1,..] (:84-95)
+//   * the parameter is updated even when the gate is false (stale momentum)
+// HBM traffic per element: read p,g,m,v + write p,m,v = 28 B (the roofline of this kernel).
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "../../include/gsb200.h"
+
+void gsb_set_error(const char* s);
+void gsb_count_launch(int n);
+int gsb_prof_begin(int id, cudaStream_t st);
+void gsb_prof_end(int slot, cudaStream_t st);
+
+namespace {
+
+struct AdamT {
+  float* p; const float* g; float* m; float* v; const float* ppl;
+  long long numel; int row_len;
+  float step, b1, omb1, b2, omb2, eps, wd, gscale;
+  unsigned int first_block, nblocks;
+};
+struct AdamArgs { int n; AdamT t[GSB_ADAM_MAX_TENSORS]; };
+
+constexpr int kAT = 256;
+constexpr int kPerThread = 8;                     // 2 x float4
+constexpr int kPerBlock = kAT * kPerThread;       // 2048 elements
+
+__device__ __forceinline__ int find_tensor(const AdamArgs& a, unsigned int b) {
+  int k = 0;
+#pragma unroll
+  for (int i = 1; i < GSB_ADAM_MAX_TENSORS; ++i)
+    if (i < a.n && b >= a.t[i].first_block) k = i;
+  return k;
+}
+
+// flags[k] = 1 when tensor k's (scaled, decayed) gradient has any element with g*g > 0.
+// Blocks bail out as soon as the flag is already set, so the usual cost is one wave.
+__global__ void __launch_bounds__(kAT) k_adam_gate(AdamArgs a, unsigned int* flags) {
+  const int k = find_tensor(a, blockIdx.x);
+  const AdamT& t = a.t[k];
+  __shared__ unsigned int s_set;
+  if (threadIdx.x == 0) s_set = *((volatile unsigned int*)(flags + k));
+  __syncthreads();
+  if (s_set) return;
+  long long base = (long long)(blockIdx.x - t.first_block) * kPerBlock;
+  bool any = false;
+  for (int u = 0; u < kPerThread; ++u) {
+    long long e = base + (long long)u * kAT + threadIdx.x;
+    if (e < t.numel) {
+      float g = t.g[e] * t.gscale;
+      if (t.wd != 0.f) g += t.wd * t.p[e];
+      any |= (g * g > 0.f);
+    }
+  }
+  if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(flags + k, 1u);
+}
+
+__device__ __forceinline__ void adam_elem(const AdamT& t, bool gate, float lr_mul, float& p, float g, float& m,
+                                          float& v) {
+  g *= t.gscale;
+  if (t.wd != 0.f) g = __fmaf_rn(t.wd, p, g);
+  if (gate) {
+    m = __fadd_rn(__fmul_rn(m, t.b1), __fmul_rn(g, t.omb1));
+    v = __fadd_rn(__fmul_rn(v, t.b2), __fmul_rn(__fmul_rn(t.omb2, g), g));
+  }
+  float denom = __fadd_rn(__fsqrt_rn(v), t.eps);
+  float upd = __fdiv_rn(m, denom);
+  p = __fadd_rn(p, __fmul_rn(-(t.step * lr_mul), upd));
+}
+
+__global__ void __launch_bounds__(kAT) k_adam(AdamArgs a, const unsigned int* __restrict__ flags) {
+  const int k = find_tensor(a, blockIdx.x);
+  const AdamT& t = a.t[k];
+  const bool gate = flags[k] != 0;
+  const long long base = (long long)(blockIdx.x - t.first_block) * kPerBlock;
+  const bool vec = ((((uintptr_t)t.p | (uintptr_t)t.g | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0);
+  if (vec && base + kPerBlock <= t.numel) {
+#pragma unroll
+    for (int u = 0; u < kPerThread / 4; ++u) {
+      long long e = base + ((long long)u * kAT + threadIdx.x) * 4;
+      float4 p = *reinterpret_cast<float4*>(t.p + e);
+      float4 g = __ldg(reinterpret_cast<const float4*>(t.g + e));
+      float4 m = *reinterpret_cast<float4*>(t.m + e);
+      float4 v = *reinterpret_cast<float4*>(t.v + e);
+      float l0 = 1.f, l1 = 1.f, l2 = 1.f, l3 = 1.f;
+      if (t.ppl) {
+        l0 = __ldg(t.ppl + e / t.row_len); l1 = __ldg(t.ppl + (e + 1) / t.row_len);
+        l2 = __ldg(t.ppl + (e + 2) / t.row_len); l3 = __ldg(t.ppl + (e + 3) / t.row_len);
+      }
+      adam_elem(t, gate, l0, p.x, g.x, m.x, v.x);
+      adam_elem(t, gate, l1, p.y, g.y, m.y, v.y);
+      adam_elem(t, gate, l2, p.z, g.z, m.z, v.z);
+      adam_elem(t, gate, l3, p.w, g.w, m.w, v.w);
+      *reinterpret_cast<float4*>(t.p + e) = p;
+      *reinterpret_cast<float4*>(t.m + e) = m;
+      *reinterpret_cast<float4*>(t.v + e) = v;
+    }
+  } else {
+    for (int u = 0; u < kPerThread; ++u) {
+      long long e = base + (long long)u * kAT + threadIdx.x;
+      if (e < t.numel) {
+        float p = t.p[e], m = t.m[e], v = t.v[e];
+        float l = t.ppl ? t.ppl[e / t.row_len] : 1.f;
+        adam_elem(t, gate, l, p, t.g[e], m, v);
+        t.p[e] = p; t.m[e] = m; t.v[e] = v;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" GSB_API int gsb_adam_step(int32_t n, const GsbAdamTensor* ts, uint32_t* flags, gsb_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n < 0 || n > GSB_ADAM_MAX_TENSORS || (n > 0 && (!ts || !flags))) {
+    gsb_set_error("gsb_adam_step: bad argument");
+    return GSB_ERR_INVALID;
+  }
+  if (n == 0) return GSB_OK;
+  AdamArgs a;
+  a.n = n;
+  unsigned int nb = 0;
+  for (int i = 0; i < n; ++i) {
+    const GsbAdamTensor& s = ts[i];
+    if (!s.param || !s.grad || !s.exp_avg || !s.exp_avg_sq || s.numel < 0 || s.row_len <= 0) {
+      gsb_set_error("gsb_adam_step: null tensor / bad shape");
+      return GSB_ERR_INVALID;
+    }
+    AdamT& t = a.t[i];
+    t.p = s.param; t.g = s.grad; t.m = s.exp_avg; t.v = s.exp_avg_sq; t.ppl = s.per_point_lr;
+    t.numel = s.numel; t.row_len = s.row_len;
+    t.step = (float)s.step_size;
+    t.b1 = (float)s.beta1; t.omb1 = (float)(1.0 - s.beta1);
+    t.b2 = (float)s.beta2; t.omb2 = (float)(1.0 - s.beta2);
+    t.eps = (float)s.eps; t.wd = (float)s.weight_decay; t.gscale = s.grad_scale;
+    t.first_block = nb;
+    t.nblocks = (unsigned int)((s.numel + kPerBlock - 1) / kPerBlock);
+    nb += t.nblocks;
+  }
+  for (int i = n; i < GSB_ADAM_MAX_TENSORS; ++i) { a.t[i] = a.t[0]; a.t[i].first_block = 0xffffffffu; a.t[i].nblocks = 0; }
+  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, st);
+  if (e == cudaSuccess && nb > 0) {
+    gsb_count_launch(2);
+    int slot = gsb_prof_begin(GSB_K_ADAM, st);
+    k_adam_gate<<<nb, kAT, 0, st>>>(a, flags);
+    k_adam<<<nb, kAT, 0, st>>>(a, flags);
+    gsb_prof_end(slot, st);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "gsb_adam_step: %s", cudaGetErrorString(e));
+    gsb_set_error(buf);
+    return GSB_ERR_CUDA;
+  }
+  return GSB_OK;
+}

@@ -1,0 +1,237 @@
+// Fused SSIM / L1 loss kernels for sm_100a (C ABI in include/gsb200.h).
+//
+// Replaces fused_ssim.fused_ssim (/root/reference/train.py:39-43,172-173; an empty submodule,
+// rahul-goel/fused-ssim @ a7c48d6) whose semantics are those of the reference's PyTorch fallback
+// /root/reference/utils/loss_utils.py:55-85: 11x11 Gaussian window sigma 1.5, zero "same"
+// padding, C1 = 0.01^2, C2 = 0.03^2, per-channel (depthwise), mean over all elements -- plus
+// l1_loss (/root/reference/utils/loss_utils.py:39-40) and the combine of train.py:176.
+//
+// One CTA = one 16x16 output tile of one channel: the (16+10)^2 halo of both images is staged in
+// shared memory once, the 11-tap window is applied separably (horizontal into shared memory,
+// vertical in registers), so HBM traffic is the compulsory read of the two images plus the three
+// partial-derivative maps written for the backward.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "../../include/gsb200.h"
+
+void gsb_set_error(const char* s);
+void gsb_count_launch(int n);
+int gsb_prof_begin(int id, cudaStream_t st);
+void gsb_prof_end(int slot, cudaStream_t st);
+
+namespace {
+
+constexpr int TS = 16;          // tile edge
+constexpr int HALO = 5;
+constexpr int TE = TS + 2 * HALO;   // 26
+constexpr float C1 = 0.01f * 0.01f;
+constexpr float C2 = 0.03f * 0.03f;
+
+// normalised 1-D window exp(-(x-5)^2 / 4.5), built like loss_utils.gaussian() (fp32 sum)
+__constant__ float c_win[11];
+bool g_win_ready = false;
+
+int ensure_window() {
+  if (g_win_ready) return 0;
+  float w[11], s = 0.f;
+  for (int i = 0; i < 11; ++i) { w[i] = (float)exp(-(double)((i - 5) * (i - 5)) / 4.5); s += w[i]; }
+  for (int i = 0; i < 11; ++i) w[i] /= s;
+  if (cudaMemcpyToSymbol(c_win, w, sizeof(w)) != cudaSuccess) return -1;
+  g_win_ready = true;
+  return 0;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (threadIdx.x < 32) {
+    r = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;   // valid in thread 0
+}
+
+// img planes [BC][H][W].  maps (optional) [3][BC][H][W].  sums[0] += sum|a-b| (if do_l1),
+// sums[1] += sum ssim.
+__global__ void __launch_bounds__(256)
+k_ssim_fwd(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
+           double* __restrict__ sums, float* __restrict__ maps, size_t plane_total, int do_l1) {
+  __shared__ float sA[TE][TE + 1], sB[TE][TE + 1];
+  __shared__ float sH[5][TE][TS + 1];
+  __shared__ float red[8];
+  const int bc = blockIdx.z;
+  const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
+  const float* p1 = img1 + (size_t)bc * H * W;
+  const float* p2 = img2 + (size_t)bc * H * W;
+  for (int k = threadIdx.x; k < TE * TE; k += 256) {
+    int r = k / TE, c = k - r * TE;
+    int y = y0 + r - HALO, x = x0 + c - HALO;
+    bool in = (x >= 0 && x < W && y >= 0 && y < H);
+    sA[r][c] = in ? __ldg(p1 + (size_t)y * W + x) : 0.f;
+    sB[r][c] = in ? __ldg(p2 + (size_t)y * W + x) : 0.f;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < TE * TS; k += 256) {
+    int r = k / TS, c = k - r * TS;
+    float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 11; ++t) {
+      float w = c_win[t], a = sA[r][c + t], b = sB[r][c + t];
+      m1 += w * a; m2 += w * b; e11 += w * a * a; e22 += w * b * b; e12 += w * a * b;
+    }
+    sH[0][r][c] = m1; sH[1][r][c] = m2; sH[2][r][c] = e11; sH[3][r][c] = e22; sH[4][r][c] = e12;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int x = x0 + tx, y = y0 + ty;
+  float ssim_v = 0.f, l1_v = 0.f;
+  if (x < W && y < H) {
+    float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 11; ++t) {
+      float w = c_win[t];
+      mu1 += w * sH[0][ty + t][tx]; mu2 += w * sH[1][ty + t][tx]; e11 += w * sH[2][ty + t][tx];
+      e22 += w * sH[3][ty + t][tx]; e12 += w * sH[4][ty + t][tx];
+    }
+    float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+    float s1 = e11 - mu1_sq, s2 = e22 - mu2_sq, s12 = e12 - mu12;
+    float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2, B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
+    float inv = 1.f / (B1 * B2);
+    ssim_v = A1 * A2 * inv;
+    if (maps) {
+      size_t o = (size_t)bc * H * W + (size_t)y * W + x;
+      maps[o] = 2.f * mu2 * (A2 - A1) * inv - ssim_v * 2.f * mu1 * (B2 - B1) * inv;   // d/dmu1
+      maps[plane_total + o] = -ssim_v / B2;                                        // d/dE[x^2]
+      maps[2 * plane_total + o] = 2.f * A1 * inv;                                  // d/dE[xy]
+    }
+    if (do_l1) l1_v = fabsf(sA[ty + HALO][tx + HALO] - sB[ty + HALO][tx + HALO]);
+  }
+  float s = block_sum(ssim_v, red);
+  if (threadIdx.x == 0) atomicAdd(sums + 1, (double)s);
+  if (do_l1) {
+    __syncthreads();
+    float l = block_sum(l1_v, red);
+    if (threadIdx.x == 0) atomicAdd(sums + 0, (double)l);
+  }
+}
+
+// out = ssim_scale * (conv(m_mu) + 2 x conv(m_s1) + y conv(m_s12)) [* *dyn_scale] + l1_scale * sign(x-y)
+__global__ void __launch_bounds__(256)
+k_ssim_bwd(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
+           const float* __restrict__ maps, size_t plane_total, float ssim_scale,
+           const float* __restrict__ dyn_scale, float l1_scale, float* __restrict__ out) {
+  __shared__ float sM[3][TE][TE + 1];
+  __shared__ float sH[3][TE][TS + 1];
+  const int bc = blockIdx.z;
+  const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
+  const size_t pbase = (size_t)bc * H * W;
+  for (int k = threadIdx.x; k < TE * TE; k += 256) {
+    int r = k / TE, c = k - r * TE;
+    int y = y0 + r - HALO, x = x0 + c - HALO;
+    bool in = (x >= 0 && x < W && y >= 0 && y < H);
+    size_t o = pbase + (size_t)y * W + x;
+    sM[0][r][c] = in ? __ldg(maps + o) : 0.f;
+    sM[1][r][c] = in ? __ldg(maps + plane_total + o) : 0.f;
+    sM[2][r][c] = in ? __ldg(maps + 2 * plane_total + o) : 0.f;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < TE * TS; k += 256) {
+    int r = k / TS, c = k - r * TS;
+    float a = 0.f, b = 0.f, d = 0.f;
+#pragma unroll
+    for (int t = 0; t < 11; ++t) {
+      float w = c_win[t];
+      a += w * sM[0][r][c + t]; b += w * sM[1][r][c + t]; d += w * sM[2][r][c + t];
+    }
+    sH[0][r][c] = a; sH[1][r][c] = b; sH[2][r][c] = d;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int x = x0 + tx, y = y0 + ty;
+  if (x < W && y < H) {
+    float a = 0.f, b = 0.f, d = 0.f;
+#pragma unroll
+    for (int t = 0; t < 11; ++t) {
+      float w = c_win[t];
+      a += w * sH[0][ty + t][tx]; b += w * sH[1][ty + t][tx]; d += w * sH[2][ty + t][tx];
+    }
+    size_t o = pbase + (size_t)y * W + x;
+    float xv = img1[o], yv = img2[o];
+    float sc = ssim_scale * (dyn_scale ? *dyn_scale : 1.f);
+    float g = sc * (a + 2.f * xv * b + yv * d);
+    if (l1_scale != 0.f) {
+      float df = xv - yv;
+      g += l1_scale * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
+    }
+    out[o] = g;
+  }
+}
+
+int check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return GSB_OK;
+  char buf[256];
+  snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  gsb_set_error(buf);
+  return GSB_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" GSB_API int gsb_ssim_forward(int32_t BC, int32_t H, int32_t W, const float* img1, const float* img2,
+                                double* ssim_sum2, float* maps, gsb_stream_t stream) {
+  if (BC <= 0 || H <= 0 || W <= 0 || !img1 || !img2 || !ssim_sum2) { gsb_set_error("gsb_ssim_forward: bad argument"); return GSB_ERR_INVALID; }
+  if (ensure_window()) return check(cudaGetLastError(), "window upload");
+  dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS, BC);
+  gsb_count_launch(1);
+  int slot = gsb_prof_begin(GSB_K_LOSS_FWD, (cudaStream_t)stream);
+  k_ssim_fwd<<<grid, 256, 0, (cudaStream_t)stream>>>(H, W, img1, img2, ssim_sum2, maps, (size_t)BC * H * W, 0);
+  gsb_prof_end(slot, (cudaStream_t)stream);
+  return check(cudaGetLastError(), "k_ssim_fwd");
+}
+
+extern "C" GSB_API int gsb_ssim_backward(int32_t BC, int32_t H, int32_t W, const float* img1, const float* img2,
+                                 const float* maps, float scale_host, const float* dL_dmean_scale,
+                                 float* dL_dimg1, gsb_stream_t stream) {
+  if (BC <= 0 || H <= 0 || W <= 0 || !img1 || !img2 || !maps || !dL_dimg1) { gsb_set_error("gsb_ssim_backward: bad argument"); return GSB_ERR_INVALID; }
+  if (ensure_window()) return check(cudaGetLastError(), "window upload");
+  dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS, BC);
+  gsb_count_launch(1);
+  int slot = gsb_prof_begin(GSB_K_LOSS_BWD, (cudaStream_t)stream);
+  k_ssim_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(H, W, img1, img2, maps, (size_t)BC * H * W, scale_host,
+                                                     dL_dmean_scale, 0.f, dL_dimg1);
+  gsb_prof_end(slot, (cudaStream_t)stream);
+  return check(cudaGetLastError(), "k_ssim_bwd");
+}
+
+extern "C" GSB_API int gsb_loss_forward(int32_t C, int32_t H, int32_t W, const float* img, const float* gt,
+                                double* sums, float* maps, gsb_stream_t stream) {
+  if (C <= 0 || H <= 0 || W <= 0 || !img || !gt || !sums || !maps) { gsb_set_error("gsb_loss_forward: bad argument"); return GSB_ERR_INVALID; }
+  if (ensure_window()) return check(cudaGetLastError(), "window upload");
+  dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS, C);
+  gsb_count_launch(1);
+  int slot = gsb_prof_begin(GSB_K_LOSS_FWD, (cudaStream_t)stream);
+  k_ssim_fwd<<<grid, 256, 0, (cudaStream_t)stream>>>(H, W, img, gt, sums, maps, (size_t)C * H * W, 1);
+  gsb_prof_end(slot, (cudaStream_t)stream);
+  return check(cudaGetLastError(), "k_loss_fwd");
+}
+
+extern "C" GSB_API int gsb_loss_backward(int32_t C, int32_t H, int32_t W, const float* img, const float* gt,
+                                 const float* maps, float lambda_dssim, float* dL_dimg, gsb_stream_t stream) {
+  if (C <= 0 || H <= 0 || W <= 0 || !img || !gt || !maps || !dL_dimg) { gsb_set_error("gsb_loss_backward: bad argument"); return GSB_ERR_INVALID; }
+  if (ensure_window()) return check(cudaGetLastError(), "window upload");
+  const double N = (double)C * H * W;
+  dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS, C);
+  gsb_count_launch(1);
+  int slot = gsb_prof_begin(GSB_K_LOSS_BWD, (cudaStream_t)stream);
+  k_ssim_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(H, W, img, gt, maps, (size_t)C * H * W,
+                                                     (float)(-(double)lambda_dssim / N), nullptr,
+                                                     (float)((1.0 - (double)lambda_dssim) / N), dL_dimg);
+  gsb_prof_end(slot, (cudaStream_t)stream);
+  return check(cudaGetLastError(), "k_loss_bwd");
+}

@@ -1,0 +1,1012 @@
+// B200 (sm_100a) differentiable Gaussian rasterizer: kernels + C ABI (include/gsb200.h).
+//
+// Pipeline (one view):
+//   k_setup_cam        camera/pose constants -> one CamConst in HBM (read by every block)
+//   k_preprocess       fused pose transform + activations + EWA projection + SH->RGB, 128-bit
+//                      coalesced loads staged through shared memory; writes packed splat records
+//   cub sort           depth keys (32 bit) -> depth order                     [library: cub]
+//   cub scan           tile counts in depth order -> offsets, R
+//   k_duplicate        (tile id, gaussian id) instances emitted in depth order, lossless culling
+//   cub sort           stable sort on the tile bits only (13 bits at 1080p)   [library: cub]
+//   k_ranges_gather    per-tile ranges + gather of the splat records into contiguous per-tile
+//                      slabs (3 x float4 per instance)
+//   k_blend_fwd        one CTA per 16x16 tile, one warp per 8x4 sub-tile; slab chunks staged in
+//                      shared memory; per-warp ballot-compacted sub-tile culling
+//   k_blend_bwd        back-to-front replay; 9 gradients per (warp, Gaussian) reduced with a
+//                      transposing butterfly (14 shuffles) then 9 RED.ADD.F32
+//   k_preprocess_bwd   analytic backward to the model's own tensors + in-kernel pose-gradient
+//                      reduction; k_pose_finalize chains it to dL/dP[7]
+//
+// Reference behaviour: SURVEY.md Appendix A; call site /root/reference/gaussian_renderer/__init__.py:60-135.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gsb200.h"
+#include "gs_math.cuh"
+
+using namespace gsb;
+
+// ------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+#define GSB_CUDA(x)                                                                       \
+  do {                                                                                    \
+    cudaError_t e_ = (x);                                                                 \
+    if (e_ != cudaSuccess) {                                                              \
+      snprintf(g_err, sizeof(g_err), "%s:%d %s: %s", __FILE__, __LINE__, #x,              \
+               cudaGetErrorString(e_));                                                   \
+      return GSB_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+#define GSB_REQUIRE(cond, msg)                                                            \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      snprintf(g_err, sizeof(g_err), "%s:%d invalid argument: %s", __FILE__, __LINE__, msg); \
+      return GSB_ERR_INVALID;                                                             \
+    }                                                                                     \
+  } while (0)
+
+extern "C" GSB_API const char* gsb_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------
+// optional per-kernel timing (CUDA events on the launching stream) and launch counting
+// ------------------------------------------------------------------------------------------
+static bool g_prof_on = false;
+static unsigned long long g_launches = 0;
+struct ProfRec { cudaEvent_t a, b; int id; };
+static ProfRec g_prof[8192];
+static int g_prof_n = 0, g_prof_cap = 0;
+void gsb_count_launch(int n) { g_launches += (unsigned long long)n; }
+int gsb_prof_begin(int id, cudaStream_t st) {
+  if (!g_prof_on || g_prof_n >= 8192) return -1;
+  if (g_prof_n >= g_prof_cap) {
+    cudaEventCreate(&g_prof[g_prof_n].a);
+    cudaEventCreate(&g_prof[g_prof_n].b);
+    g_prof_cap = g_prof_n + 1;
+  }
+  g_prof[g_prof_n].id = id;
+  cudaEventRecord(g_prof[g_prof_n].a, st);
+  return g_prof_n++;
+}
+void gsb_prof_end(int slot, cudaStream_t st) {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].b, st);
+}
+extern "C" GSB_API void gsb_profile_enable(int on) { g_prof_on = on != 0; g_prof_n = 0; }
+// ms_sum[id] += elapsed, count[id] += 1 for every recorded interval; resets the record list.
+extern "C" GSB_API int gsb_profile_collect(double* ms_sum, int64_t* count, int n_ids) {
+  for (int i = 0; i < g_prof_n; ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(g_prof[i].b) != cudaSuccess) return GSB_ERR_CUDA;
+    if (cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b) != cudaSuccess) return GSB_ERR_CUDA;
+    if (g_prof[i].id >= 0 && g_prof[i].id < n_ids) { ms_sum[g_prof[i].id] += ms; count[g_prof[i].id] += 1; }
+  }
+  g_prof_n = 0;
+  return GSB_OK;
+}
+extern "C" GSB_API uint64_t gsb_launch_count(void) { return g_launches; }
+struct ProfScope {
+  int slot; cudaStream_t st;
+  ProfScope(int id, cudaStream_t s, int launches = 1) : st(s) { gsb_count_launch(launches); slot = gsb_prof_begin(id, s); }
+  ~ProfScope() { gsb_prof_end(slot, st); }
+};
+extern "C" GSB_API int gsb_abi_version(void) { return 1; }
+void gsb_set_error(const char* s) { snprintf(g_err, sizeof(g_err), "%s", s); }
+
+// ------------------------------------------------------------------------------------------
+// buffer layouts
+// ------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+constexpr int kThreads = 256;
+constexpr int kRowPad = 49;      // shared-memory SH row stride (48 + 1, conflict-free)
+constexpr int kChunk = 256;      // slab entries staged per step in the blend kernels
+
+struct GeomView {
+  CamConst* cam;
+  float4* xyAB;        // x, y, conic A, conic B
+  float4* Codq;        // conic C, opacity, depth, cull threshold
+  float4* rgbr;        // r, g, b, radius
+  uint2* rect;         // x: rx0 | rx1<<16   y: ry0 | ry1<<16
+  uint32_t* tiles;     // tile instances per Gaussian (after culling)
+  uint32_t* dkey;      // depth key (0xFFFFFFFF: not visible)
+  uint32_t* iota;
+  uint32_t* dkey_s;
+  uint32_t* order;     // Gaussian ids in depth order
+  uint32_t* offs;      // inclusive scan of tiles[order[j]]
+  uint8_t* clamped;
+  float4* dacc;        // [3P] backward accumulators
+  float* pose_part;    // [nblocks*16]
+  float* pose_acc;     // [16]
+  uint32_t* nrend;     // [1]
+  void* cub_tmp;
+  size_t cub_bytes;
+  size_t total;
+};
+
+static size_t cub_bytes_geom(int P) {
+  size_t a = 0, b = 0;
+  uint32_t* k = nullptr;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, k, k, k, k, P, 0, 32);
+  cub::DeviceScan::InclusiveSum(nullptr, b, k, k, P);
+  return (a > b ? a : b) + 1024;
+}
+
+static GeomView geom_view(void* base, int P) {
+  GeomView v;
+  size_t off = 0;
+  char* p = (char*)base;
+  size_t Pp = (size_t)(P > 0 ? P : 1);
+  auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += align_up(bytes); return r; };
+  v.cam = (CamConst*)take(sizeof(CamConst));
+  v.xyAB = (float4*)take(Pp * 16);
+  v.Codq = (float4*)take(Pp * 16);
+  v.rgbr = (float4*)take(Pp * 16);
+  v.rect = (uint2*)take(Pp * 8);
+  v.tiles = (uint32_t*)take(Pp * 4);
+  v.dkey = (uint32_t*)take(Pp * 4);
+  v.iota = (uint32_t*)take(Pp * 4);
+  v.dkey_s = (uint32_t*)take(Pp * 4);
+  v.order = (uint32_t*)take(Pp * 4);
+  v.offs = (uint32_t*)take(Pp * 4);
+  v.clamped = (uint8_t*)take(Pp);
+  v.dacc = (float4*)take(Pp * 48);
+  size_t nb = (Pp + kThreads - 1) / kThreads;
+  v.pose_part = (float*)take(nb * 16 * 4);
+  v.pose_acc = (float*)take(16 * 4);
+  v.nrend = (uint32_t*)take(4);
+  v.cub_bytes = cub_bytes_geom((int)Pp);
+  v.cub_tmp = take(v.cub_bytes);
+  v.total = off;
+  return v;
+}
+
+struct BinView {
+  uint32_t* keys;
+  uint32_t* keys_s;
+  uint32_t* vals;
+  uint32_t* vals_s;
+  float4* s0;          // x, y, A, B
+  float4* s1;          // C, opacity, cull threshold, gaussian id (bits)
+  float4* s2;          // r, g, b, -
+  uint2* ranges;       // [tiles]
+  void* cub_tmp;
+  size_t cub_bytes;
+  size_t total;
+};
+
+static int tile_bits(int ntiles) {
+  int b = 1;
+  while ((1 << b) < ntiles + 1) ++b;
+  return b;
+}
+
+static BinView bin_view(void* base, int64_t R, int W, int H) {
+  BinView v;
+  size_t off = 0;
+  char* p = (char*)base;
+  size_t Rp = (size_t)(R > 0 ? R : 1);
+  int ntiles = ((W + kBlock - 1) / kBlock) * ((H + kBlock - 1) / kBlock);
+  auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += align_up(bytes); return r; };
+  v.keys = (uint32_t*)take(Rp * 4);
+  v.keys_s = (uint32_t*)take(Rp * 4);
+  v.vals = (uint32_t*)take(Rp * 4);
+  v.vals_s = (uint32_t*)take(Rp * 4);
+  v.s0 = (float4*)take(Rp * 16);
+  v.s1 = (float4*)take(Rp * 16);
+  v.s2 = (float4*)take(Rp * 16);
+  v.ranges = (uint2*)take((size_t)ntiles * 8);
+  size_t a = 0;
+  uint32_t* k = nullptr;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, k, k, k, k, (int)Rp, 0, tile_bits(ntiles));
+  v.cub_bytes = a + 1024;
+  v.cub_tmp = take(v.cub_bytes);
+  v.total = off;
+  return v;
+}
+
+struct ImgView {
+  float* final_T;
+  uint32_t* n_contrib;
+  size_t total;
+};
+static ImgView img_view(void* base, int W, int H) {
+  ImgView v;
+  size_t hw = (size_t)W * H;
+  char* p = (char*)base;
+  v.final_T = (float*)p;
+  v.n_contrib = (uint32_t*)(p ? p + align_up(hw * 4) : nullptr);
+  v.total = 2 * align_up(hw * 4);
+  return v;
+}
+
+extern "C" GSB_API size_t gsb_geom_bytes(int32_t P) { return geom_view(nullptr, P).total; }
+extern "C" GSB_API size_t gsb_binning_bytes(int64_t R, int32_t W, int32_t H) { return bin_view(nullptr, R, W, H).total; }
+extern "C" GSB_API size_t gsb_image_bytes(int32_t W, int32_t H) { return img_view(nullptr, W, H).total; }
+
+// ------------------------------------------------------------------------------------------
+// kernel parameter blocks
+// ------------------------------------------------------------------------------------------
+struct InPtrs {
+  int P;
+  const float* means;
+  const float* scales;
+  const float* rots;
+  const float* opac;
+  const float* sh_dc;
+  const float* sh_rest;
+  const float* colors;
+  const float* cov3D;
+  int sh_packed;
+  int vec_ok;       // all base pointers 16-byte aligned
+  int exact_cull;
+};
+
+// ------------------------------------------------------------------------------------------
+// k_setup_cam
+// ------------------------------------------------------------------------------------------
+__global__ void k_setup_cam(CamConst* out, const float* V, const float* Pm, const float* campos,
+                            const float* pose, int W, int H, float tanfovx, float tanfovy,
+                            float scale_mod, int D, int M, int raw_params) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  CamConst c;
+  for (int i = 0; i < 16; ++i) { c.V[i] = V[i]; c.Pm[i] = Pm[i]; }
+  for (int i = 0; i < 3; ++i) c.campos[i] = campos[i];
+  c.tanfovx = tanfovx; c.tanfovy = tanfovy;
+  c.fx = W / (2.0f * tanfovx); c.fy = H / (2.0f * tanfovy);
+  c.scale_mod = scale_mod; c.W = W; c.H = H;
+  c.gx = (W + kBlock - 1) / kBlock; c.gy = (H + kBlock - 1) / kBlock;
+  c.D = D; c.M = M; c.raw_params = raw_params; c.pose_on = 0;
+  for (int i = 0; i < 9; ++i) c.Rc[i] = (i % 4 == 0) ? 1.f : 0.f;
+  c.tc[0] = c.tc[1] = c.tc[2] = 0.f;
+  c.qc[0] = 1.f; c.qc[1] = c.qc[2] = c.qc[3] = 0.f;
+  if (pose) pose_to_const(pose, c);
+  *out = c;
+}
+
+// ------------------------------------------------------------------------------------------
+// staging helpers: copy `n` contiguous floats global -> shared (or back) with 128-bit accesses
+// ------------------------------------------------------------------------------------------
+// dst index of source element k is (k / row) * stride + col0 + (k % row)
+__device__ __forceinline__ void stage_in(float* sm, const float* __restrict__ src, int n, int row,
+                                         int stride, int col0, bool vec) {
+  if (vec) {
+    int n4 = n >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int k = threadIdx.x; k < n4; k += blockDim.x) {
+      float4 v = __ldg(s4 + k);
+      int e = 4 * k;
+      int r = e / row, c = e - r * row;
+      float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        sm[r * stride + col0 + c] = vv[u];
+        if (++c == row) { c = 0; ++r; }
+      }
+    }
+    for (int e = 4 * n4 + threadIdx.x; e < n; e += blockDim.x) {
+      int r = e / row, c = e - r * row;
+      sm[r * stride + col0 + c] = __ldg(src + e);
+    }
+  } else {
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      int r = e / row, c = e - r * row;
+      sm[r * stride + col0 + c] = __ldg(src + e);
+    }
+  }
+}
+
+__device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* sm, int n, int row,
+                                          int stride, int col0, bool vec) {
+  if (vec) {
+    int n4 = n >> 2;
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int k = threadIdx.x; k < n4; k += blockDim.x) {
+      int e = 4 * k;
+      int r = e / row, c = e - r * row;
+      float vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        vv[u] = sm[r * stride + col0 + c];
+        if (++c == row) { c = 0; ++r; }
+      }
+      d4[k] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+    for (int e = 4 * n4 + threadIdx.x; e < n; e += blockDim.x) {
+      int r = e / row, c = e - r * row;
+      dst[e] = sm[r * stride + col0 + c];
+    }
+  } else {
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      int r = e / row, c = e - r * row;
+      dst[e] = sm[r * stride + col0 + c];
+    }
+  }
+}
+
+// Shared-memory layout of the two per-Gaussian kernels (dynamic):
+//   cam   : CamConst
+//   sh    : [256][49]  (dc in cols 0..2, rest in cols 3..47)
+//   geo   : [256][13]  (xyz 0..2, scale 3..5, quat 6..9, opacity 10; stride 13 is conflict-free)
+constexpr int kGeoPad = 13;
+constexpr size_t kPrepSmem = sizeof(CamConst) + 16 + (size_t)kThreads * (kRowPad + kGeoPad) * 4;
+
+__device__ __forceinline__ void load_block_inputs(const InPtrs& in, int first, int nv, bool use_sh,
+                                                  int D, int M, float* sm_sh, float* sm_geo) {
+  bool vec = in.vec_ok != 0;
+  stage_in(sm_geo, in.means + (size_t)3 * first, 3 * nv, 3, kGeoPad, 0, vec);
+  if (in.scales) stage_in(sm_geo, in.scales + (size_t)3 * first, 3 * nv, 3, kGeoPad, 3, vec);
+  if (in.rots) stage_in(sm_geo, in.rots + (size_t)4 * first, 4 * nv, 4, kGeoPad, 6, vec);
+  stage_in(sm_geo, in.opac + first, nv, 1, kGeoPad, 10, vec);
+  if (use_sh) {
+    if (in.sh_packed) {
+      stage_in(sm_sh, in.sh_dc + (size_t)3 * M * first, 3 * M * nv, 3 * M, kRowPad, 0, vec);
+    } else {
+      stage_in(sm_sh, in.sh_dc + (size_t)3 * first, 3 * nv, 3, kRowPad, 0, vec);
+      if (D > 0 && M > 1)
+        stage_in(sm_sh, in.sh_rest + (size_t)3 * (M - 1) * first, 3 * (M - 1) * nv, 3 * (M - 1),
+                 kRowPad, 3, vec);
+    }
+  }
+}
+
+__device__ __forceinline__ void read_gauss(const float* sm_geo, int t, bool has_sr, GaussIn& g) {
+  const float* r = sm_geo + t * kGeoPad;
+  g.m[0] = r[0]; g.m[1] = r[1]; g.m[2] = r[2];
+  if (has_sr) {
+    g.sc[0] = r[3]; g.sc[1] = r[4]; g.sc[2] = r[5];
+    g.q[0] = r[6]; g.q[1] = r[7]; g.q[2] = r[8]; g.q[3] = r[9];
+  } else {
+    g.sc[0] = g.sc[1] = g.sc[2] = 1.f;
+    g.q[0] = 1.f; g.q[1] = g.q[2] = g.q[3] = 0.f;
+  }
+  g.op = r[10];
+}
+
+__device__ __forceinline__ uint32_t count_or_emit_tiles(const Proj& p, float qthr, int W, int H, int gx,
+                                                        bool cull, uint32_t* keys, uint32_t* vals,
+                                                        uint32_t id) {
+  uint32_t n = 0;
+  for (int ty = p.ry0; ty < p.ry1; ++ty)
+    for (int tx = p.rx0; tx < p.rx1; ++tx) {
+      bool keep = true;
+      if (cull) {
+        float x0 = (float)(tx * kBlock), y0 = (float)(ty * kBlock);
+        float x1 = fminf(x0 + kBlock - 1, (float)(W - 1)), y1 = fminf(y0 + kBlock - 1, (float)(H - 1));
+        keep = rect_may_contribute(p.x, p.y, p.A, p.B, p.C, qthr, x0, y0, x1, y1);
+      }
+      if (keep) {
+        if (keys) { keys[n] = (uint32_t)(ty * gx + tx); vals[n] = id; }
+        ++n;
+      }
+    }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_preprocess
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CamConst* cam = reinterpret_cast<CamConst*>(smem_raw);
+  float* sm_sh = reinterpret_cast<float*>(smem_raw + ((sizeof(CamConst) + 15) / 16) * 16);
+  float* sm_geo = sm_sh + kThreads * kRowPad;
+  {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(gv.cam);
+    uint32_t* d = reinterpret_cast<uint32_t*>(cam);
+    for (int k = threadIdx.x; k < (int)(sizeof(CamConst) / 4); k += blockDim.x) d[k] = s[k];
+  }
+  int first = blockIdx.x * kThreads;
+  int nv = min(kThreads, in.P - first);
+  bool use_sh = in.colors == nullptr;
+  __syncthreads();
+  load_block_inputs(in, first, nv, use_sh, cam->D, cam->M, sm_sh, sm_geo);
+  __syncthreads();
+  int t = threadIdx.x;
+  if (t >= nv) return;
+  int i = first + t;
+  GaussIn g;
+  read_gauss(sm_geo, t, in.scales != nullptr, g);
+  Proj p;
+  project_geometry(*cam, g, in.cov3D ? in.cov3D + (size_t)6 * i : nullptr, p);
+  float qthr = -1.f;
+  uint32_t ntiles = 0;
+  if (p.visible) {
+    if (use_sh) {
+      project_color(*cam, sm_sh + t * kRowPad, sm_sh + t * kRowPad + 3, p);
+    } else {
+      p.rgb[0] = in.colors[3 * i]; p.rgb[1] = in.colors[3 * i + 1]; p.rgb[2] = in.colors[3 * i + 2];
+    }
+    qthr = cull_threshold(p.opacity);
+    ntiles = count_or_emit_tiles(p, qthr, cam->W, cam->H, cam->gx, in.exact_cull != 0, nullptr, nullptr, 0);
+  } else {
+    p.x = p.y = p.A = p.B = p.C = 0.f; p.rgb[0] = p.rgb[1] = p.rgb[2] = 0.f;
+  }
+  gv.xyAB[i] = make_float4(p.x, p.y, p.A, p.B);
+  gv.Codq[i] = make_float4(p.C, p.opacity, p.depth, qthr);
+  gv.rgbr[i] = make_float4(p.rgb[0], p.rgb[1], p.rgb[2], (float)p.radius);
+  gv.rect[i] = make_uint2((uint32_t)p.rx0 | ((uint32_t)p.rx1 << 16), (uint32_t)p.ry0 | ((uint32_t)p.ry1 << 16));
+  gv.tiles[i] = ntiles;
+  gv.dkey[i] = p.visible ? __float_as_uint(p.depth) : 0xFFFFFFFFu;
+  gv.iota[i] = (uint32_t)i;
+  gv.clamped[i] = (uint8_t)p.clamped;
+  radii[i] = p.radius;
+}
+
+struct TilesInOrder {
+  const uint32_t* tiles;
+  const uint32_t* order;
+  __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& j) const { return tiles[order[j]]; }
+};
+
+__global__ void k_store_total(const uint32_t* offs, int P, uint32_t* nrend) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *nrend = P > 0 ? offs[P - 1] : 0u;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_duplicate: one thread per depth-ordered Gaussian
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_duplicate(int P, GeomView gv, BinView bv, int W, int H, int gx, int exact_cull, uint32_t R) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= P) return;
+  uint32_t i = gv.order[j];
+  uint32_t n = gv.tiles[i];
+  if (n == 0) return;
+  uint32_t off = gv.offs[j] - n;
+  if (off + n > R) return;   // defensive: never write past the binning buffer
+  float4 a = gv.xyAB[i], b = gv.Codq[i];
+  uint2 rc = gv.rect[i];
+  Proj p;
+  p.x = a.x; p.y = a.y; p.A = a.z; p.B = a.w; p.C = b.x;
+  p.rx0 = rc.x & 0xFFFF; p.rx1 = rc.x >> 16; p.ry0 = rc.y & 0xFFFF; p.ry1 = rc.y >> 16;
+  count_or_emit_tiles(p, b.w, W, H, gx, exact_cull != 0, bv.keys + off, bv.vals + off, i);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_ranges_gather: tile ranges + contiguous per-tile slabs
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_ranges_gather(uint32_t R, GeomView gv, BinView bv) {
+  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= R) return;
+  uint32_t tile = bv.keys_s[e];
+  uint32_t i = bv.vals_s[e];
+  if (e == 0 || bv.keys_s[e - 1] != tile) bv.ranges[tile].x = e;
+  if (e == R - 1 || bv.keys_s[e + 1] != tile) bv.ranges[tile].y = e + 1;
+  float4 a = gv.xyAB[i], b = gv.Codq[i], c = gv.rgbr[i];
+  bv.s0[e] = a;
+  bv.s1[e] = make_float4(b.x, b.y, b.w, __uint_as_float(i));
+  bv.s2[e] = make_float4(c.x, c.y, c.z, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------
+// blend
+// ------------------------------------------------------------------------------------------
+struct PairEval { float dx, dy, power, G, alpha; };
+
+__device__ __forceinline__ PairEval pair_eval(const float4& e0, const float4& e1, float fx, float fy) {
+  PairEval r;
+  r.dx = e0.x - fx;
+  r.dy = e0.y - fy;
+  r.power = -0.5f * (e0.z * r.dx * r.dx + e1.x * r.dy * r.dy) - e0.w * r.dx * r.dy;
+  r.G = __expf(r.power);
+  r.alpha = fminf(0.99f, e1.y * r.G);
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_blend_fwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
+            const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+            float* __restrict__ out_color, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+  __shared__ float4 sm0[kChunk], sm1[kChunk], sm2[kChunk];
+  const int tile = blockIdx.x;
+  const int tx = tile % gx, ty = tile / gx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sx0 = tx * kBlock + (warp & 1) * 8, sy0 = ty * kBlock + (warp >> 1) * 4;
+  const int px = sx0 + (lane & 7), py = sy0 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const float fx = (float)px, fy = (float)py;
+  const float rx0 = (float)sx0, ry0 = (float)sy0;
+  const float rx1 = (float)min(sx0 + 7, W - 1), ry1 = (float)min(sy0 + 3, H - 1);
+  const uint2 rg = ranges[tile];
+  const int n = (int)(rg.y - rg.x);
+  float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f;
+  uint32_t last = 0;
+  bool done = !inside;
+  bool wdone = !(sx0 < W && sy0 < H);
+  for (int base = 0; base < n; base += kChunk) {
+    const int cnt = min(kChunk, n - base);
+    if ((int)threadIdx.x < cnt) {
+      size_t e = (size_t)rg.x + base + threadIdx.x;
+      sm0[threadIdx.x] = s0[e];
+      sm1[threadIdx.x] = s1[e];
+      sm2[threadIdx.x] = s2[e];
+    }
+    __syncthreads();
+    if (!wdone) {
+      for (int b = 0; b < cnt; b += 32) {
+        const int j = b + lane;
+        bool hit = false;
+        if (j < cnt) {
+          float4 e0 = sm0[j], e1 = sm1[j];
+          hit = rect_may_contribute(e0.x, e0.y, e0.z, e0.w, e1.x, e1.z, rx0, ry0, rx1, ry1);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+          const int k = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float4 e0 = sm0[b + k], e1 = sm1[b + k];
+          PairEval pe = pair_eval(e0, e1, fx, fy);
+          bool valid = !done && pe.power <= 0.f && pe.alpha >= kAlphaMin;
+          float testT = T * (1.f - pe.alpha);
+          if (valid && testT < kTEps) { done = true; valid = false; }
+          if (valid) {
+            const float4 c = sm2[b + k];
+            float w = pe.alpha * T;
+            Cr += c.x * w; Cg += c.y * w; Cb += c.z * w;
+            T = testT;
+            last = (uint32_t)(base + b + k + 1);
+          }
+        }
+        if (__all_sync(0xffffffffu, done)) { wdone = true; break; }
+      }
+    }
+    if (__syncthreads_and(wdone)) break;
+  }
+  if (inside) {
+    size_t pix = (size_t)py * W + px, hw = (size_t)W * H;
+    final_T[pix] = T;
+    n_contrib[pix] = last;
+    out_color[pix] = Cr + T * bg[0];
+    out_color[hw + pix] = Cg + T * bg[1];
+    out_color[2 * hw + pix] = Cb + T * bg[2];
+  }
+}
+
+// Reduce 9 per-lane values over the warp with 14 shuffles.  On return, lane l with (l & 3) == 0
+// holds the total of v[l >> 2] in v[0]; every lane holds the total of v[8] in v[8].
+__device__ __forceinline__ void warp_reduce9(float* v, int lane) {
+  const unsigned full = 0xffffffffu;
+  float b[4], c[2], d;
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float send = hi ? v[k] : v[k + 4];
+      float keep = hi ? v[k + 4] : v[k];
+      b[k] = keep + __shfl_xor_sync(full, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float send = hi ? b[k] : b[k + 2];
+      float keep = hi ? b[k + 2] : b[k];
+      c[k] = keep + __shfl_xor_sync(full, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+    float send = hi ? c[0] : c[1];
+    float keep = hi ? c[1] : c[0];
+    d = keep + __shfl_xor_sync(full, send, 4);
+  }
+  d += __shfl_xor_sync(full, d, 2);
+  d += __shfl_xor_sync(full, d, 1);
+  v[0] = d;
+  float e = v[8];
+  e += __shfl_xor_sync(full, e, 16);
+  e += __shfl_xor_sync(full, e, 8);
+  e += __shfl_xor_sync(full, e, 4);
+  e += __shfl_xor_sync(full, e, 2);
+  e += __shfl_xor_sync(full, e, 1);
+  v[8] = e;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_blend_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
+            const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+            const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
+            const float* __restrict__ dL_dpix, float* __restrict__ dacc) {
+  __shared__ float4 sm0[kChunk], sm1[kChunk], sm2[kChunk];
+  __shared__ int s_bmax;
+  const int tile = blockIdx.x;
+  const int tx = tile % gx, ty = tile / gx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sx0 = tx * kBlock + (warp & 1) * 8, sy0 = ty * kBlock + (warp >> 1) * 4;
+  const int px = sx0 + (lane & 7), py = sy0 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const float fx = (float)px, fy = (float)py;
+  const float rx0 = (float)sx0, ry0 = (float)sy0;
+  const float rx1 = (float)min(sx0 + 7, W - 1), ry1 = (float)min(sy0 + 3, H - 1);
+  const uint2 rg = ranges[tile];
+  const size_t pix = (size_t)py * W + px, hw = (size_t)W * H;
+  const float T_final = inside ? final_T[pix] : 0.f;
+  const int last_contrib = inside ? (int)n_contrib[pix] : 0;
+  float dLr = 0.f, dLg = 0.f, dLb = 0.f;
+  if (inside) { dLr = dL_dpix[pix]; dLg = dL_dpix[hw + pix]; dLb = dL_dpix[2 * hw + pix]; }
+  const float bg_dot = bg[0] * dLr + bg[1] * dLg + bg[2] * dLb;
+  int wmax = last_contrib;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  if (threadIdx.x == 0) s_bmax = 0;
+  __syncthreads();
+  if (lane == 0) atomicMax(&s_bmax, wmax);
+  __syncthreads();
+  const int bmax = s_bmax;
+  float T = T_final;
+  float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, last_alpha = 0.f, last_r = 0.f, last_g = 0.f, last_b = 0.f;
+  const int nchunks = (bmax + kChunk - 1) / kChunk;
+  for (int ch = nchunks - 1; ch >= 0; --ch) {
+    const int base = ch * kChunk;
+    const int cnt = min(kChunk, bmax - base);
+    if ((int)threadIdx.x < cnt) {
+      size_t e = (size_t)rg.x + base + threadIdx.x;
+      sm0[threadIdx.x] = s0[e];
+      sm1[threadIdx.x] = s1[e];
+      sm2[threadIdx.x] = s2[e];
+    }
+    __syncthreads();
+    if (base < wmax) {
+      for (int b = (cnt - 1) & ~31; b >= 0; b -= 32) {
+        if (base + b >= wmax) continue;
+        const int j = b + lane;
+        bool hit = false;
+        if (j < cnt && base + j < wmax) {
+          float4 e0 = sm0[j], e1 = sm1[j];
+          hit = rect_may_contribute(e0.x, e0.y, e0.z, e0.w, e1.x, e1.z, rx0, ry0, rx1, ry1);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+          const int k = 31 - __clz(mask);
+          mask &= ~(1u << k);
+          const int pos = base + b + k;
+          const float4 e0 = sm0[b + k], e1 = sm1[b + k];
+          PairEval pe = pair_eval(e0, e1, fx, fy);
+          const bool valid = inside && pos < last_contrib && pe.power <= 0.f && pe.alpha >= kAlphaMin;
+          if (!__any_sync(0xffffffffu, valid)) continue;
+          float v[9];
+#pragma unroll
+          for (int u = 0; u < 9; ++u) v[u] = 0.f;
+          if (valid) {
+            const float4 c = sm2[b + k];
+            T = T / (1.f - pe.alpha);
+            const float dchannel_dcolor = pe.alpha * T;
+            acc_r = last_alpha * last_r + (1.f - last_alpha) * acc_r; last_r = c.x;
+            acc_g = last_alpha * last_g + (1.f - last_alpha) * acc_g; last_g = c.y;
+            acc_b = last_alpha * last_b + (1.f - last_alpha) * acc_b; last_b = c.z;
+            float dL_dalpha = (c.x - acc_r) * dLr + (c.y - acc_g) * dLg + (c.z - acc_b) * dLb;
+            dL_dalpha *= T;
+            last_alpha = pe.alpha;
+            dL_dalpha += (-T_final / (1.f - pe.alpha)) * bg_dot;
+            const float dL_dG = e1.y * dL_dalpha;
+            const float gdx = pe.G * pe.dx, gdy = pe.G * pe.dy;
+            v[0] = dL_dG * (-gdx * e0.z - gdy * e0.w);
+            v[1] = dL_dG * (-gdy * e1.x - gdx * e0.w);
+            v[2] = -0.5f * gdx * pe.dx * dL_dG;
+            v[3] = -gdx * pe.dy * dL_dG;
+            v[4] = -0.5f * gdy * pe.dy * dL_dG;
+            v[5] = pe.G * dL_dalpha;
+            v[6] = dchannel_dcolor * dLr;
+            v[7] = dchannel_dcolor * dLg;
+            v[8] = dchannel_dcolor * dLb;
+          }
+          warp_reduce9(v, lane);
+          float* dst = dacc + (size_t)__float_as_uint(e1.w) * 12;
+          if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), v[0]);
+          if (lane == 1) atomicAdd(dst + 8, v[8]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_preprocess_bwd
+// ------------------------------------------------------------------------------------------
+struct OutPtrs {
+  float* dmeans; float* dmeans2D; float* dscales; float* drots; float* dopac;
+  float* dsh_dc; float* dsh_rest; float* dcolors; float* dcov3D;
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_preprocess_bwd(InPtrs in, GeomView gv, const int* __restrict__ radii_unused, OutPtrs out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CamConst* cam = reinterpret_cast<CamConst*>(smem_raw);
+  float* sm_sh = reinterpret_cast<float*>(smem_raw + ((sizeof(CamConst) + 15) / 16) * 16);
+  float* sm_geo = sm_sh + kThreads * kRowPad;
+  __shared__ float s_pose[8][16];
+  {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(gv.cam);
+    uint32_t* d = reinterpret_cast<uint32_t*>(cam);
+    for (int k = threadIdx.x; k < (int)(sizeof(CamConst) / 4); k += blockDim.x) d[k] = s[k];
+  }
+  const int first = blockIdx.x * kThreads;
+  const int nv = min(kThreads, in.P - first);
+  const bool use_sh = in.colors == nullptr;
+  const bool vec = in.vec_ok != 0;
+  __syncthreads();
+  const int D = cam->D, M = cam->M;
+  load_block_inputs(in, first, nv, use_sh, D, M, sm_sh, sm_geo);
+  __syncthreads();
+  const int t = threadIdx.x;
+  const int i = first + t;
+  float pa[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) pa[k] = 0.f;
+  GaussGrad gg;
+  float ddc[3] = {0.f, 0.f, 0.f};
+  float drest[45];
+#pragma unroll
+  for (int k = 0; k < 45; ++k) drest[k] = 0.f;
+  gg.dm[0] = gg.dm[1] = gg.dm[2] = 0.f; gg.dsc[0] = gg.dsc[1] = gg.dsc[2] = 0.f;
+  gg.dq[0] = gg.dq[1] = gg.dq[2] = gg.dq[3] = 0.f; gg.dop = 0.f;
+  gg.dmeans2D[0] = gg.dmeans2D[1] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) gg.dcov3D[k] = 0.f;
+  gg.dcolor[0] = gg.dcolor[1] = gg.dcolor[2] = 0.f;
+  if (t < nv) {
+    float4 d0 = gv.dacc[3 * (size_t)i], d1 = gv.dacc[3 * (size_t)i + 1], d2 = gv.dacc[3 * (size_t)i + 2];
+    float ds[9] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x};
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) any |= (ds[k] != 0.f);
+    if (any && gv.tiles[i] > 0) {
+      GaussIn g;
+      read_gauss(sm_geo, t, in.scales != nullptr, g);
+      Proj p;
+      project_geometry(*cam, g, in.cov3D ? in.cov3D + (size_t)6 * i : nullptr, p);
+      if (p.visible) {
+        p.clamped = gv.clamped[i];
+        project_bwd(*cam, g, p, sm_sh + t * kRowPad + 3, use_sh, in.cov3D != nullptr, ds, gg, ddc, drest, pa);
+      }
+    }
+  }
+  __syncthreads();   // everyone is done reading sm_sh / sm_geo
+  if (t < nv) {
+    float* r = sm_geo + t * kGeoPad;
+    r[0] = gg.dm[0]; r[1] = gg.dm[1]; r[2] = gg.dm[2];
+    r[3] = gg.dsc[0]; r[4] = gg.dsc[1]; r[5] = gg.dsc[2];
+    r[6] = gg.dq[0]; r[7] = gg.dq[1]; r[8] = gg.dq[2]; r[9] = gg.dq[3];
+    r[10] = gg.dop;
+    float* s = sm_sh + t * kRowPad;
+    s[0] = ddc[0]; s[1] = ddc[1]; s[2] = ddc[2];
+#pragma unroll
+    for (int k = 0; k < 45; ++k) s[3 + k] = drest[k];
+    if (out.dmeans2D) {
+      out.dmeans2D[3 * (size_t)i] = gg.dmeans2D[0];
+      out.dmeans2D[3 * (size_t)i + 1] = gg.dmeans2D[1];
+      out.dmeans2D[3 * (size_t)i + 2] = 0.f;
+    }
+    if (out.dcolors) {
+      out.dcolors[3 * (size_t)i] = gg.dcolor[0]; out.dcolors[3 * (size_t)i + 1] = gg.dcolor[1];
+      out.dcolors[3 * (size_t)i + 2] = gg.dcolor[2];
+    }
+    if (out.dcov3D) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) out.dcov3D[6 * (size_t)i + k] = gg.dcov3D[k];
+    }
+  }
+  __syncthreads();
+  if (out.dmeans) stage_out(out.dmeans + (size_t)3 * first, sm_geo, 3 * nv, 3, kGeoPad, 0, vec);
+  if (out.dscales) stage_out(out.dscales + (size_t)3 * first, sm_geo, 3 * nv, 3, kGeoPad, 3, vec);
+  if (out.drots) stage_out(out.drots + (size_t)4 * first, sm_geo, 4 * nv, 4, kGeoPad, 6, vec);
+  if (out.dopac) stage_out(out.dopac + first, sm_geo, nv, 1, kGeoPad, 10, vec);
+  if (use_sh && out.dsh_dc) {
+    if (in.sh_packed) {
+      stage_out(out.dsh_dc + (size_t)3 * M * first, sm_sh, 3 * M * nv, 3 * M, kRowPad, 0, vec);
+    } else {
+      stage_out(out.dsh_dc + (size_t)3 * first, sm_sh, 3 * nv, 3, kRowPad, 0, vec);
+      if (M > 1 && out.dsh_rest)
+        stage_out(out.dsh_rest + (size_t)3 * (M - 1) * first, sm_sh, 3 * (M - 1) * nv, 3 * (M - 1),
+                  kRowPad, 3, vec);
+    }
+  }
+  // pose-gradient partials: warp shuffle, then across the 8 warps
+  if (cam->pose_on) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float v = pa[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_pose[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += s_pose[w][threadIdx.x];
+      gv.pose_part[(size_t)blockIdx.x * 16 + threadIdx.x] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pose_finalize(const float* part, int nblocks, const float* pose,
+                                                       float* dpose) {
+  __shared__ float s[16][17];
+  const int k = threadIdx.x & 15, g = threadIdx.x >> 4;   // 16 groups of 16
+  float v = 0.f;
+  for (int b = g; b < nblocks; b += 16) v += part[(size_t)b * 16 + k];
+  s[g][k] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float acc[16];
+    for (int c = 0; c < 16; ++c) {
+      float a = 0.f;
+      for (int r = 0; r < 16; ++r) a += s[r][c];
+      acc[c] = a;
+    }
+    float dp[7];
+    pose_grad_finalize(pose, acc, dp);
+    for (int c = 0; c < 7; ++c) dpose[c] = dp[c];
+  }
+}
+
+__global__ void k_mark_visible(int P, const float* means, const float* V, uint8_t* present) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  float z = means[3 * i] * V[2] + means[3 * i + 1] * V[6] + means[3 * i + 2] * V[10] + V[14];
+  present[i] = z > kNear ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+static int make_inptrs(const GsbCamera* cam, const GsbGaussians* g, InPtrs& in) {
+  GSB_REQUIRE(cam && g, "null camera / gaussians");
+  GSB_REQUIRE(g->P >= 0, "P < 0");
+  GSB_REQUIRE(cam->width > 0 && cam->height > 0, "image size");
+  GSB_REQUIRE(cam->width <= 65535 * kBlock && cam->height <= 65535 * kBlock, "image too large");
+  GSB_REQUIRE(cam->sh_degree >= 0 && cam->sh_degree <= 3, "sh_degree must be 0..3");
+  GSB_REQUIRE(cam->sh_coeffs >= 1 && cam->sh_coeffs <= 16, "sh_coeffs must be 1..16");
+  GSB_REQUIRE((cam->sh_degree + 1) * (cam->sh_degree + 1) <= cam->sh_coeffs || g->colors_precomp,
+              "active SH degree exceeds stored coefficients");
+  GSB_REQUIRE(cam->bg && cam->viewmatrix && cam->projmatrix && cam->campos, "null camera tensor");
+  GSB_REQUIRE(g->means3D && g->opacities, "means3D / opacities are required");
+  GSB_REQUIRE((g->sh_dc != nullptr) != (g->colors_precomp != nullptr),
+              "provide exactly one of SHs / precomputed colours");
+  GSB_REQUIRE((g->scales != nullptr && g->rotations != nullptr) != (g->cov3D_precomp != nullptr),
+              "provide exactly one of scale+rotation / precomputed 3D covariance");
+  if (g->sh_dc && !g->sh_packed && cam->sh_coeffs > 1 && cam->sh_degree > 0)
+    GSB_REQUIRE(g->sh_rest != nullptr, "sh_rest missing");
+  in.P = g->P; in.means = g->means3D; in.scales = g->scales; in.rots = g->rotations; in.opac = g->opacities;
+  in.sh_dc = g->sh_dc; in.sh_rest = g->sh_rest; in.colors = g->colors_precomp; in.cov3D = g->cov3D_precomp;
+  in.sh_packed = g->sh_packed; in.exact_cull = cam->exact_cull;
+  uintptr_t a = (uintptr_t)g->means3D | (uintptr_t)g->scales | (uintptr_t)g->rotations |
+                (uintptr_t)g->opacities | (uintptr_t)g->sh_dc | (uintptr_t)g->sh_rest;
+  in.vec_ok = (a & 15) == 0;
+  return GSB_OK;
+}
+
+static bool g_attr_set = false;
+static int ensure_attrs() {
+  if (!g_attr_set) {
+    GSB_CUDA(cudaFuncSetAttribute(k_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrepSmem));
+    GSB_CUDA(cudaFuncSetAttribute(k_preprocess_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrepSmem));
+    g_attr_set = true;
+  }
+  return GSB_OK;
+}
+
+extern "C" GSB_API int gsb_preprocess(const GsbCamera* cam, const GsbGaussians* g, void* geom, size_t geom_bytes,
+                              int32_t* radii, uint32_t* num_rendered_host, gsb_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  InPtrs in;
+  int rc = make_inptrs(cam, g, in);
+  if (rc) return rc;
+  GSB_REQUIRE(geom && radii && num_rendered_host, "null buffer");
+  const int P = g->P;
+  GeomView gv = geom_view(geom, P);
+  if (gv.total > geom_bytes) { gsb_set_error("geom buffer too small"); return GSB_ERR_CAPACITY; }
+  rc = ensure_attrs();
+  if (rc) return rc;
+  gsb_count_launch(1);
+  k_setup_cam<<<1, 32, 0, st>>>(gv.cam, cam->viewmatrix, cam->projmatrix, cam->campos, g->pose, cam->width,
+                                cam->height, cam->tanfovx, cam->tanfovy, cam->scale_modifier, cam->sh_degree,
+                                cam->sh_coeffs, g->raw_params);
+  if (P == 0) {
+    GSB_CUDA(cudaMemsetAsync(gv.nrend, 0, 4, st));
+  } else {
+    const int nb = (P + kThreads - 1) / kThreads;
+    { ProfScope ps(GSB_K_PREPROCESS, st); k_preprocess<<<nb, kThreads, kPrepSmem, st>>>(in, gv, radii); }
+    size_t tb = gv.cub_bytes;
+    { ProfScope ps(GSB_K_SORT_DEPTH, st, 0);
+      GSB_CUDA(cub::DeviceRadixSort::SortPairs(gv.cub_tmp, tb, gv.dkey, gv.dkey_s, gv.iota, gv.order, P, 0, 32, st)); }
+    cub::CountingInputIterator<uint32_t> cnt(0);
+    TilesInOrder op{gv.tiles, gv.order};
+    cub::TransformInputIterator<uint32_t, TilesInOrder, cub::CountingInputIterator<uint32_t>> it(cnt, op);
+    tb = gv.cub_bytes;
+    { ProfScope ps(GSB_K_SCAN, st, 1);
+      GSB_CUDA(cub::DeviceScan::InclusiveSum(gv.cub_tmp, tb, it, gv.offs, P, st));
+      k_store_total<<<1, 32, 0, st>>>(gv.offs, P, gv.nrend); }
+  }
+  GSB_CUDA(cudaMemcpyAsync(num_rendered_host, gv.nrend, 4, cudaMemcpyDeviceToHost, st));
+  GSB_CUDA(cudaGetLastError());
+  return GSB_OK;
+}
+
+extern "C" GSB_API int gsb_render(const GsbCamera* cam, int32_t P, void* geom, void* binning, size_t binning_bytes,
+                          int64_t R, void* image, float* out_color, gsb_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  GSB_REQUIRE(cam && geom && binning && image && out_color, "null buffer");
+  GSB_REQUIRE(R >= 0 && R < (int64_t)0x7fffffff, "R out of range");
+  const int W = cam->width, H = cam->height;
+  const int gx = (W + kBlock - 1) / kBlock, gy = (H + kBlock - 1) / kBlock;
+  GeomView gv = geom_view(geom, P);
+  BinView bv = bin_view(binning, R, W, H);
+  if (bv.total > binning_bytes) { gsb_set_error("binning buffer too small"); return GSB_ERR_CAPACITY; }
+  ImgView iv = img_view(image, W, H);
+  GSB_CUDA(cudaMemsetAsync(bv.ranges, 0, (size_t)gx * gy * 8, st));
+  if (R > 0) {
+    { ProfScope ps(GSB_K_DUPLICATE, st);
+      k_duplicate<<<(P + kThreads - 1) / kThreads, kThreads, 0, st>>>(P, gv, bv, W, H, gx, cam->exact_cull, (uint32_t)R); }
+    size_t tb = bv.cub_bytes;
+    { ProfScope ps(GSB_K_SORT_TILE, st, 0);
+      GSB_CUDA(cub::DeviceRadixSort::SortPairs(bv.cub_tmp, tb, bv.keys, bv.keys_s, bv.vals, bv.vals_s, (int)R, 0,
+                                               tile_bits(gx * gy), st)); }
+    { ProfScope ps(GSB_K_GATHER, st);
+      k_ranges_gather<<<(unsigned)((R + kThreads - 1) / kThreads), kThreads, 0, st>>>((uint32_t)R, gv, bv); }
+  }
+  { ProfScope ps(GSB_K_BLEND_FWD, st);
+    k_blend_fwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, out_color,
+                                              iv.final_T, iv.n_contrib); }
+  GSB_CUDA(cudaGetLastError());
+  return GSB_OK;
+}
+
+extern "C" GSB_API int gsb_backward(const GsbCamera* cam, const GsbGaussians* g, void* geom, void* binning, int64_t R,
+                            void* image, const float* dL_dout, const GsbGrads* grads, gsb_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  InPtrs in;
+  int rc = make_inptrs(cam, g, in);
+  if (rc) return rc;
+  GSB_REQUIRE(geom && binning && image && dL_dout && grads, "null buffer");
+  if (g->pose) GSB_REQUIRE(grads->dL_dpose != nullptr, "dL_dpose required when pose is fused");
+  const int P = g->P, W = cam->width, H = cam->height;
+  const int gx = (W + kBlock - 1) / kBlock, gy = (H + kBlock - 1) / kBlock;
+  GeomView gv = geom_view(geom, P);
+  BinView bv = bin_view(binning, R, W, H);
+  ImgView iv = img_view(image, W, H);
+  rc = ensure_attrs();
+  if (rc) return rc;
+  if (P == 0) {
+    if (grads->dL_dpose) GSB_CUDA(cudaMemsetAsync(grads->dL_dpose, 0, 7 * 4, st));
+    return GSB_OK;
+  }
+  GSB_CUDA(cudaMemsetAsync(gv.dacc, 0, (size_t)P * 48, st));
+  if (R > 0) {
+    ProfScope ps(GSB_K_BLEND_BWD, st);
+    k_blend_bwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, iv.final_T,
+                                              iv.n_contrib, dL_dout, (float*)gv.dacc);
+  }
+  OutPtrs out;
+  out.dmeans = grads->dL_dmeans3D; out.dmeans2D = grads->dL_dmeans2D; out.dscales = grads->dL_dscales;
+  out.drots = grads->dL_drotations; out.dopac = grads->dL_dopacities; out.dsh_dc = grads->dL_dsh_dc;
+  out.dsh_rest = grads->dL_dsh_rest; out.dcolors = grads->dL_dcolors; out.dcov3D = grads->dL_dcov3D;
+  uintptr_t a = (uintptr_t)out.dmeans | (uintptr_t)out.dscales | (uintptr_t)out.drots | (uintptr_t)out.dopac |
+                (uintptr_t)out.dsh_dc | (uintptr_t)out.dsh_rest;
+  if (a & 15) in.vec_ok = 0;
+  const int nb = (P + kThreads - 1) / kThreads;
+  { ProfScope ps(GSB_K_PREPROCESS_BWD, st, g->pose ? 2 : 1);
+    k_preprocess_bwd<<<nb, kThreads, kPrepSmem, st>>>(in, gv, nullptr, out);
+    if (g->pose) k_pose_finalize<<<1, 256, 0, st>>>(gv.pose_part, nb, g->pose, grads->dL_dpose); }
+  GSB_CUDA(cudaGetLastError());
+  return GSB_OK;
+}
+
+extern "C" GSB_API int gsb_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                                const float* projmatrix, uint8_t* present, gsb_stream_t stream_) {
+  (void)projmatrix;
+  GSB_REQUIRE(P >= 0 && means3D && viewmatrix && present, "null buffer");
+  if (P > 0)
+    k_mark_visible<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(P, means3D, viewmatrix, present);
+  GSB_CUDA(cudaGetLastError());
+  return GSB_OK;
+}

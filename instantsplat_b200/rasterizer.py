@@ -1,0 +1,241 @@
+"""Drop-in for the `diff_gaussian_rasterization` package (boundary B2 of SURVEY.md section 8b) on top
+of libgsb200.so, plus the fused InstantSplat entry (`rasterize_fused`) used by `render()`.
+
+Mirrors the interface the reference calls at /root/reference/gaussian_renderer/__init__.py:14-17,
+60-78,126-135 (and the vanilla-3DGS form at gaussian_renderer/__init__3dgs.py:36-51,85-93):
+same names, argument meaning and error behaviour.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import GsbCamera, GsbGaussians, GsbGrads, check, f32c, ptr
+
+_vp = ctypes.c_void_p
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+_pinned = {}
+
+
+def _pinned_u32(device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    t = _pinned.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32).pin_memory()
+        _pinned[key] = t
+    return t
+
+
+EXACT_CULL = True   # lossless alpha<1/255 tile culling (set False for the reference's rect-only binning)
+
+
+class _State:
+    """Everything the backward needs; keeps the torch buffers alive."""
+    __slots__ = ("cam", "g", "geom", "binning", "image", "R", "keep", "P", "M", "packed", "has_pose")
+
+
+def _camera(settings: GaussianRasterizationSettings, sh_coeffs: int, keep: list) -> GsbCamera:
+    bg, vm, pm, cp = (f32c(settings.bg), f32c(settings.viewmatrix), f32c(settings.projmatrix),
+                      f32c(settings.campos))
+    keep += [bg, vm, pm, cp]
+    cam = GsbCamera()
+    cam.width, cam.height = int(settings.image_width), int(settings.image_height)
+    cam.tanfovx, cam.tanfovy = float(settings.tanfovx), float(settings.tanfovy)
+    cam.scale_modifier = float(settings.scale_modifier)
+    cam.sh_degree, cam.sh_coeffs = int(settings.sh_degree), int(sh_coeffs)
+    cam.exact_cull = 1 if EXACT_CULL else 0
+    cam.bg, cam.viewmatrix, cam.projmatrix, cam.campos = ptr(bg), ptr(vm), ptr(pm), ptr(cp)
+    return cam
+
+
+def _forward(settings, means3D, scales, rotations, opacities, sh_dc, sh_rest, sh_packed, M,
+             colors_precomp, cov3D_precomp, pose, raw_params):
+    L = _lib.lib()
+    dev = means3D.device
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    P = means3D.shape[0]
+    st = _State()
+    st.keep = []
+    st.cam = _camera(settings, M, st.keep)
+    g = GsbGaussians()
+    g.P, g.sh_packed, g.raw_params = P, int(sh_packed), int(raw_params)
+    ts = dict(means3D=means3D, scales=scales, rotations=rotations, opacities=opacities, sh_dc=sh_dc,
+              sh_rest=sh_rest, colors_precomp=colors_precomp, cov3D_precomp=cov3D_precomp, pose=pose)
+    for k, v in ts.items():
+        v = f32c(v)
+        st.keep.append(v)
+        setattr(g, k, ptr(v))
+    st.g, st.P, st.M, st.packed, st.has_pose = g, P, M, bool(sh_packed), pose is not None
+    H, W = st.cam.height, st.cam.width
+    stream = _lib.stream_ptr()
+    geom_bytes = L.gsb_geom_bytes(P)
+    st.geom = torch.empty(geom_bytes, dtype=torch.uint8, device=dev)
+    radii = torch.empty(P, dtype=torch.int32, device=dev)
+    host_r = _pinned_u32(dev)
+    check(L.gsb_preprocess(ctypes.byref(st.cam), ctypes.byref(g), st.geom.data_ptr(), geom_bytes,
+                           radii.data_ptr(), host_r.data_ptr(), stream), "gsb_preprocess")
+    torch.cuda.current_stream().synchronize()          # the one host sync: R sizes the binning buffers
+    R = int(host_r.item()) & 0xFFFFFFFF
+    st.R = R
+    bin_bytes = L.gsb_binning_bytes(R, W, H)
+    st.binning = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
+    st.image = torch.empty(L.gsb_image_bytes(W, H), dtype=torch.uint8, device=dev)
+    color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
+    check(L.gsb_render(ctypes.byref(st.cam), P, st.geom.data_ptr(), st.binning.data_ptr(), bin_bytes, R,
+                       st.image.data_ptr(), color.data_ptr(), stream), "gsb_render")
+    if settings.debug:
+        torch.cuda.synchronize()
+    return color, radii, st
+
+
+def _backward(st: _State, dL_dout, want, dev):
+    """want: dict name -> bool.  Returns dict of grad tensors (dense)."""
+    L = _lib.lib()
+    P, M = st.P, st.M
+    dL = f32c(dL_dout)
+    gr = GsbGrads()
+    out = {}
+
+    def alloc(name, shape, field):
+        t = torch.empty(shape, dtype=torch.float32, device=dev)
+        out[name] = t
+        setattr(gr, field, t.data_ptr())
+
+    alloc("means3D", (P, 3), "dL_dmeans3D")
+    alloc("means2D", (P, 3), "dL_dmeans2D")
+    alloc("opacities", (P,), "dL_dopacities")
+    if st.g.scales:
+        alloc("scales", (P, 3), "dL_dscales")
+        alloc("rotations", (P, 4), "dL_drotations")
+    if st.g.cov3D_precomp:
+        alloc("cov3D", (P, 6), "dL_dcov3D")
+    if st.g.colors_precomp:
+        alloc("colors", (P, 3), "dL_dcolors")
+    else:
+        if st.packed:
+            alloc("sh", (P, M, 3), "dL_dsh_dc")
+        else:
+            alloc("sh_dc", (P, 1, 3), "dL_dsh_dc")
+            if M > 1:
+                alloc("sh_rest", (P, M - 1, 3), "dL_dsh_rest")
+    if st.has_pose:
+        alloc("pose", (7,), "dL_dpose")
+    check(L.gsb_backward(ctypes.byref(st.cam), ctypes.byref(st.g), st.geom.data_ptr(), st.binning.data_ptr(),
+                         st.R, st.image.data_ptr(), dL.data_ptr(), ctypes.byref(gr), _lib.stream_ptr()),
+          "gsb_backward")
+    return out
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        has = lambda t: t is not None and t.numel() > 0
+        M = sh.shape[1] if has(sh) else 1
+        color, radii, st = _forward(
+            raster_settings, means3D, scales if has(scales) else None,
+            rotations if has(rotations) else None, opacities.reshape(-1) if opacities.dim() > 1 else opacities,
+            sh if has(sh) else None, None, 1, M, colors_precomp if has(colors_precomp) else None,
+            cov3Ds_precomp if has(cov3Ds_precomp) else None, None, 0)
+        ctx.st = st
+        ctx.shapes = (opacities.shape,)
+        ctx.debug = raster_settings.debug
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii):
+        st = ctx.st
+        g = _backward(st, grad_out_color, None, grad_out_color.device)
+        if ctx.debug:
+            torch.cuda.synchronize()
+        return (g["means3D"], g["means2D"], g.get("sh"), g.get("colors"),
+                g["opacities"].reshape(ctx.shapes[0]), g.get("scales"), g.get("rotations"), g.get("cov3D"),
+                None)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeFused(torch.autograd.Function):
+    """InstantSplat path with everything fused: raw model tensors + camera pose in, image out.
+    Replaces /root/reference/gaussian_renderer/__init__.py:81-135 and its autograd chain."""
+
+    @staticmethod
+    def forward(ctx, xyz, rotation, scaling, opacity, f_dc, f_rest, pose, means2D, raster_settings):
+        M = 1 + (f_rest.shape[1] if f_rest is not None and f_rest.numel() > 0 else 0)
+        color, radii, st = _forward(raster_settings, xyz, scaling, rotation, opacity.reshape(-1),
+                                    f_dc.reshape(-1, 3), f_rest if M > 1 else None, 0, M, None, None, pose, 1)
+        ctx.st = st
+        ctx.shapes = (opacity.shape, f_dc.shape, None if f_rest is None else f_rest.shape)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii):
+        st = ctx.st
+        g = _backward(st, grad_out_color, None, grad_out_color.device)
+        osh, dsh, rsh = ctx.shapes
+        g_rest = g.get("sh_rest")
+        if g_rest is None and rsh is not None:
+            g_rest = torch.zeros(rsh, dtype=torch.float32, device=grad_out_color.device)
+        return (g["means3D"], g["rotations"], g["scales"], g["opacities"].reshape(osh),
+                g["sh_dc"].reshape(dsh), g_rest, g["pose"], g["means2D"], None)
+
+
+def rasterize_fused(xyz, rotation, scaling, opacity, f_dc, f_rest, pose, means2D, raster_settings):
+    return _RasterizeFused.apply(xyz, rotation, scaling, opacity, f_dc, f_rest, pose, means2D, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            pos = f32c(positions)
+            vm, pm = f32c(rs.viewmatrix), f32c(rs.projmatrix)
+            out = torch.empty(pos.shape[0], dtype=torch.uint8, device=pos.device)
+            check(_lib.lib().gsb_mark_visible(pos.shape[0], ptr(pos), ptr(vm), ptr(pm), ptr(out),
+                                              _lib.stream_ptr()), "gsb_mark_visible")
+        return out.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        e = torch.Tensor([]).to(means3D.device)
+        return rasterize_gaussians(means3D, means2D, e if shs is None else shs,
+                                   e if colors_precomp is None else colors_precomp, opacities,
+                                   e if scales is None else scales, e if rotations is None else rotations,
+                                   e if cov3D_precomp is None else cov3D_precomp, rs)

@@ -1,0 +1,273 @@
+"""The joint pose + Gaussian optimisation inner loop of /root/reference/train.py:124-211, B200-first.
+
+One `JointTrainer.step(view)` = update_learning_rate -> render (fused pose transform + rasterizer)
+-> L1 + DSSIM loss -> backward -> (multi-GPU: NCCL sum of the flat per-Gaussian gradient buffer)
+-> per-point Adam, i.e. exactly one iteration of the reference loop, but:
+
+  * all Gaussian parameters, gradients and Adam moments live in FLAT fp32 buffers (one tensor per
+    kind, 256-byte aligned segments) so the backward kernels write gradients straight into the
+    buffer NCCL reduces, and Adam is one launch over all seven tensors;
+  * ~12 kernel launches per iteration instead of the reference's several hundred ATen launches,
+    and exactly one host sync (the instance count R that sizes the binning buffers).
+
+Multi-GPU: one process per GPU, a full replica of the cloud per GPU,
+training views sharded round-robin (view v -> rank v mod G); per step every rank renders one of
+its views, gradients are summed with one all-reduce over NVLink and scaled by 1/G inside the Adam
+kernel, so all replicas stay bit-identical.  An "iteration" in the reported iters/s is one VIEW
+(one reference iteration); one optimizer step consumes G views.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GsbCamera, GsbGaussians, GsbGrads, check
+from .per_point_adam import launch_adam
+from .scenes import Scene
+
+SEGMENTS = (("xyz", 3), ("f_dc", 3), ("f_rest", 45), ("opacity", 1), ("scaling", 3), ("rotation", 4))
+
+
+def get_expon_lr_func(lr_init, lr_final, lr_delay_steps=0, lr_delay_mult=1.0, max_steps=1000000):
+    """/root/reference/utils/general_utils.py:29-62 (host-side, fp64 numpy, unchanged semantics)."""
+
+    def helper(step):
+        if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+            return 0.0
+        if lr_delay_steps > 0:
+            delay_rate = lr_delay_mult + (1 - lr_delay_mult) * np.sin(
+                0.5 * np.pi * np.clip(step / lr_delay_steps, 0, 1))
+        else:
+            delay_rate = 1.0
+        t = np.clip(step / max_steps, 0, 1)
+        return delay_rate * np.exp(np.log(lr_init) * (1 - t) + np.log(lr_final) * t)
+
+    return helper
+
+
+class OptimConfig:
+    """/root/reference/arguments/__init__.py:73-94 defaults."""
+    iterations = 30_000
+    position_lr_init = 0.00016
+    position_lr_final = 0.0000016
+    position_lr_delay_mult = 0.01
+    position_lr_max_steps = 30_000
+    feature_lr = 0.0025
+    opacity_lr = 0.05
+    scaling_lr = 0.005
+    rotation_lr = 0.001
+    lambda_dssim = 0.2
+    pp_optimizer = True
+    optim_pose = True
+    spatial_lr_scale = 1.0
+
+
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
+class JointTrainer:
+    def __init__(self, scene: Scene, device, gt_images: Optional[torch.Tensor] = None,
+                 cfg: Optional[OptimConfig] = None, world_size: int = 1, rank: int = 0,
+                 process_group=None):
+        self.cfg = cfg or OptimConfig()
+        self.dev = torch.device(device)
+        self.world_size, self.rank, self.pg = world_size, rank, process_group
+        self.P = P = scene.P
+        self.W, self.H = scene.width, scene.height
+        self.sh_degree = scene.sh_degree
+        self.n_views = scene.n_views
+        # ---- flat buffers
+        offs, total = {}, 0
+        for name, k in SEGMENTS:
+            offs[name] = total
+            total += _align(P * k)
+        self.offs, self.total = offs, total
+        self.params = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.grads = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        for name, k in SEGMENTS:
+            self.view(self.params, name).copy_(scene.params[name].reshape(P, k).to(self.dev))
+        self.poses = scene.poses.to(self.dev).float().contiguous()              # [n_views,7]
+        self.pose_grad = torch.zeros_like(self.poses)
+        self.pose_m = torch.zeros_like(self.poses)
+        self.pose_v = torch.zeros_like(self.poses)
+        self.per_point_lr = None
+        if self.cfg.pp_optimizer and scene.per_point_lr is not None:
+            self.per_point_lr = scene.per_point_lr.to(self.dev).float().reshape(P).contiguous()
+        self.gt = None if gt_images is None else gt_images.to(self.dev).float().contiguous()
+        # ---- camera constants (identity view, reference gaussian_renderer/__init__.py:55-59)
+        from .camera import projection_matrix
+        self.tanfovx, self.tanfovy = math.tan(scene.fovx * 0.5), math.tan(scene.fovy * 0.5)
+        self.viewmatrix = torch.eye(4, device=self.dev)
+        self.projmatrix = projection_matrix(0.01, 100.0, scene.fovx, scene.fovy).t().contiguous().to(self.dev)
+        self.campos = torch.zeros(3, device=self.dev)
+        self.bg = scene.bg.to(self.dev).float().contiguous()
+        # ---- scratch
+        L = _lib.lib()
+        self.geom_bytes = L.gsb_geom_bytes(P)
+        self.geom = torch.empty(self.geom_bytes, dtype=torch.uint8, device=self.dev)
+        self.image_buf = torch.empty(L.gsb_image_bytes(self.W, self.H), dtype=torch.uint8, device=self.dev)
+        self.binning = None
+        self.bin_bytes = 0
+        self.radii = torch.empty(P, dtype=torch.int32, device=self.dev)
+        self.color = torch.empty(3, self.H, self.W, dtype=torch.float32, device=self.dev)
+        self.dL_dimg = torch.empty_like(self.color)
+        self.maps = torch.empty(3, 3, self.H, self.W, dtype=torch.float32, device=self.dev)
+        self.sums = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        self.host_r = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.flags = torch.zeros(8, dtype=torch.int32, device=self.dev)
+        self.iteration = 0
+        self.opt_step = 0
+        self.last_R = 0
+        self.exact_cull = True
+        c = self.cfg
+        self.xyz_sched = get_expon_lr_func(c.position_lr_init * c.spatial_lr_scale,
+                                           c.position_lr_final * c.spatial_lr_scale,
+                                           lr_delay_mult=c.position_lr_delay_mult,
+                                           max_steps=c.position_lr_max_steps)
+        self.cam_sched = get_expon_lr_func(c.rotation_lr * 0.1, c.rotation_lr * 0.001,
+                                           lr_delay_mult=c.position_lr_delay_mult, max_steps=c.iterations)
+        self._keep = None
+
+    # ------------------------------------------------------------------------------------------
+    def view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        k = dict(SEGMENTS)[name]
+        o = self.offs[name]
+        return flat[o:o + self.P * k].view(self.P, k)
+
+    def my_views(self) -> List[int]:
+        from .parallel import shard_views
+        return shard_views(self.n_views, self.world_size, self.rank)
+
+    def _cam(self) -> GsbCamera:
+        cam = GsbCamera()
+        cam.width, cam.height = self.W, self.H
+        cam.tanfovx, cam.tanfovy, cam.scale_modifier = self.tanfovx, self.tanfovy, 1.0
+        cam.sh_degree, cam.sh_coeffs = self.sh_degree, 16
+        cam.exact_cull = 1 if self.exact_cull else 0
+        cam.bg, cam.viewmatrix = self.bg.data_ptr(), self.viewmatrix.data_ptr()
+        cam.projmatrix, cam.campos = self.projmatrix.data_ptr(), self.campos.data_ptr()
+        return cam
+
+    def _gauss(self, view: int) -> GsbGaussians:
+        g = GsbGaussians()
+        g.P, g.sh_packed, g.raw_params = self.P, 0, 1
+        p = self.params
+        g.means3D = self.view(p, "xyz").data_ptr()
+        g.scales = self.view(p, "scaling").data_ptr()
+        g.rotations = self.view(p, "rotation").data_ptr()
+        g.opacities = self.view(p, "opacity").data_ptr()
+        g.sh_dc = self.view(p, "f_dc").data_ptr()
+        g.sh_rest = self.view(p, "f_rest").data_ptr()
+        g.pose = self.poses[view].data_ptr()
+        return g
+
+    # ------------------------------------------------------------------------------------------
+    def render(self, view: int) -> torch.Tensor:
+        """Forward only (also the first half of step())."""
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        cam, g = self._cam(), self._gauss(view)
+        check(L.gsb_preprocess(ctypes.byref(cam), ctypes.byref(g), self.geom.data_ptr(), self.geom_bytes,
+                               self.radii.data_ptr(), self.host_r.data_ptr(), st), "gsb_preprocess")
+        torch.cuda.current_stream().synchronize()
+        R = int(self.host_r.item()) & 0xFFFFFFFF
+        self.last_R = R
+        need = L.gsb_binning_bytes(R, self.W, self.H)
+        if need > self.bin_bytes:
+            self.bin_bytes = int(need * 1.25)
+            self.binning = torch.empty(self.bin_bytes, dtype=torch.uint8, device=self.dev)
+        check(L.gsb_render(ctypes.byref(cam), self.P, self.geom.data_ptr(), self.binning.data_ptr(),
+                           self.bin_bytes, R, self.image_buf.data_ptr(), self.color.data_ptr(), st), "gsb_render")
+        self._keep = (cam, g)
+        return self.color
+
+    def loss_and_backward(self, view: int, gt: torch.Tensor) -> None:
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        cam, g = self._keep
+        self.sums.zero_()
+        check(L.gsb_loss_forward(3, self.H, self.W, self.color.data_ptr(), gt.data_ptr(), self.sums.data_ptr(),
+                                 self.maps.data_ptr(), st), "gsb_loss_forward")
+        check(L.gsb_loss_backward(3, self.H, self.W, self.color.data_ptr(), gt.data_ptr(), self.maps.data_ptr(),
+                                  float(self.cfg.lambda_dssim), self.dL_dimg.data_ptr(), st), "gsb_loss_backward")
+        gr = GsbGrads()
+        gd = self.grads
+        gr.dL_dmeans3D = self.view(gd, "xyz").data_ptr()
+        gr.dL_dscales = self.view(gd, "scaling").data_ptr()
+        gr.dL_drotations = self.view(gd, "rotation").data_ptr()
+        gr.dL_dopacities = self.view(gd, "opacity").data_ptr()
+        gr.dL_dsh_dc = self.view(gd, "f_dc").data_ptr()
+        gr.dL_dsh_rest = self.view(gd, "f_rest").data_ptr()
+        self.pose_grad.zero_()
+        gr.dL_dpose = self.pose_grad[view].data_ptr()
+        check(L.gsb_backward(ctypes.byref(cam), ctypes.byref(g), self.geom.data_ptr(), self.binning.data_ptr(),
+                             self.last_R, self.image_buf.data_ptr(), self.dL_dimg.data_ptr(), ctypes.byref(gr), st),
+              "gsb_backward")
+
+    def loss_value(self) -> torch.Tensor:
+        n = 3 * self.H * self.W
+        lam = self.cfg.lambda_dssim
+        return (1.0 - lam) * self.sums[0] / n + lam * (1.0 - self.sums[1] / n)
+
+    def reduce_grads(self) -> None:
+        if self.world_size > 1:
+            from .parallel import allreduce_sum_
+            allreduce_sum_((self.grads, self.pose_grad), self.pg)
+
+    def optimizer_step(self) -> None:
+        """PerPointAdam.step over the 6 Gaussian tensors + the pose table in one launch
+        (param groups and LRs of /root/reference/scene/gaussian_model.py:203-243)."""
+        c = self.cfg
+        self.opt_step += 1
+        t = self.opt_step
+        b1, b2, eps = 0.9, 0.999, 1e-15
+        corr = (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
+        lrs = dict(xyz=self.xyz_sched(self.iteration), f_dc=c.feature_lr * 10, f_rest=c.feature_lr / 20.0 * 10,
+                   opacity=c.opacity_lr, scaling=c.scaling_lr * 10, rotation=c.rotation_lr * 10)
+        gs = 1.0 / self.world_size
+        entries = []
+        for name, k in SEGMENTS:
+            entries.append(dict(param=self.view(self.params, name), grad=self.view(self.grads, name),
+                                exp_avg=self.view(self.exp_avg, name), exp_avg_sq=self.view(self.exp_avg_sq, name),
+                                per_point_lr=self.per_point_lr if name == "xyz" else None, row_len=k,
+                                step_size=lrs[name] * corr, beta1=b1, beta2=b2, eps=eps, weight_decay=0.0,
+                                grad_scale=gs))
+        if c.optim_pose:
+            entries.append(dict(param=self.poses, grad=self.pose_grad, exp_avg=self.pose_m, exp_avg_sq=self.pose_v,
+                                per_point_lr=None, row_len=7, step_size=self.cam_sched(self.iteration) * corr,
+                                beta1=b1, beta2=b2, eps=eps, weight_decay=0.0, grad_scale=gs))
+        launch_adam(entries, self.flags)
+
+    def step(self, view: int, gt: Optional[torch.Tensor] = None) -> None:
+        """One reference iteration on `view` (train.py:140-211)."""
+        self.iteration += 1
+        if gt is None:
+            gt = self.gt[view]
+        self.render(view)
+        self.loss_and_backward(view, gt)
+        self.reduce_grads()
+        self.optimizer_step()
+
+    # ------------------------------------------------------------------------------------------
+    def algorithmic_bytes(self) -> Dict[str, float]:
+        """SURVEY.md section 8(d) per-kernel algorithmic HBM bytes for the last step (fp32)."""
+        P, R, HW = self.P, self.last_R, self.W * self.H
+        T = ((self.W + 15) // 16) * ((self.H + 15) // 16)
+        K = (self.sh_degree + 1) ** 2
+        V = P
+        return dict(
+            preprocess_fwd=P * (12 + 12 + 16 + 4) + V * 12 * K + V * (8 + 4 + 16 + 12 + 4) + P * 4,
+            blend_fwd=R * 40 + HW * 20 + T * 8,
+            blend_bwd=R * 40 + HW * 20 + T * 8 + V * 36,
+            preprocess_bwd=P * 44 + V * (12 * K + 36) + P * 44 + V * 12 * K,
+            loss=HW * 36,
+            adam=59 * P * 28 + P * 4,
+        )

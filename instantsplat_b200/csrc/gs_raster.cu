@@ -869,13 +869,15 @@ static int make_inptrs(const GsbCamera* cam, const GsbGaussians* g, InPtrs& in) 
   GSB_REQUIRE((cam->sh_degree + 1) * (cam->sh_degree + 1) <= cam->sh_coeffs || g->colors_precomp,
               "active SH degree exceeds stored coefficients");
   GSB_REQUIRE(cam->bg && cam->viewmatrix && cam->projmatrix && cam->campos, "null camera tensor");
-  GSB_REQUIRE(g->means3D && g->opacities, "means3D / opacities are required");
-  GSB_REQUIRE((g->sh_dc != nullptr) != (g->colors_precomp != nullptr),
-              "provide exactly one of SHs / precomputed colours");
-  GSB_REQUIRE((g->scales != nullptr && g->rotations != nullptr) != (g->cov3D_precomp != nullptr),
-              "provide exactly one of scale+rotation / precomputed 3D covariance");
-  if (g->sh_dc && !g->sh_packed && cam->sh_coeffs > 1 && cam->sh_degree > 0)
-    GSB_REQUIRE(g->sh_rest != nullptr, "sh_rest missing");
+  if (g->P > 0) {   // an empty cloud may come with null tensors
+    GSB_REQUIRE(g->means3D && g->opacities, "means3D / opacities are required");
+    GSB_REQUIRE((g->sh_dc != nullptr) != (g->colors_precomp != nullptr),
+                "provide exactly one of SHs / precomputed colours");
+    GSB_REQUIRE((g->scales != nullptr && g->rotations != nullptr) != (g->cov3D_precomp != nullptr),
+                "provide exactly one of scale+rotation / precomputed 3D covariance");
+    if (g->sh_dc && !g->sh_packed && cam->sh_coeffs > 1 && cam->sh_degree > 0)
+      GSB_REQUIRE(g->sh_rest != nullptr, "sh_rest missing");
+  }
   in.P = g->P; in.means = g->means3D; in.scales = g->scales; in.rots = g->rotations; in.opac = g->opacities;
   in.sh_dc = g->sh_dc; in.sh_rest = g->sh_rest; in.colors = g->colors_precomp; in.cov3D = g->cov3D_precomp;
   in.sh_packed = g->sh_packed; in.exact_cull = cam->exact_cull;
@@ -901,7 +903,7 @@ extern "C" GSB_API int gsb_preprocess(const GsbCamera* cam, const GsbGaussians* 
   InPtrs in;
   int rc = make_inptrs(cam, g, in);
   if (rc) return rc;
-  GSB_REQUIRE(geom && radii && num_rendered_host, "null buffer");
+  GSB_REQUIRE(geom && (radii || g->P == 0) && num_rendered_host, "null buffer");
   const int P = g->P;
   GeomView gv = geom_view(geom, P);
   if (gv.total > geom_bytes) { gsb_set_error("geom buffer too small"); return GSB_ERR_CAPACITY; }

@@ -187,7 +187,7 @@ class _RasterizeFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz, rotation, scaling, opacity, f_dc, f_rest, pose, means2D, raster_settings):
-        M = 1 + (f_rest.shape[1] if f_rest is not None and f_rest.numel() > 0 else 0)
+        M = 1 + (f_rest.shape[1] if f_rest is not None and f_rest.dim() == 3 else 0)
         color, radii, st = _forward(raster_settings, xyz, scaling, rotation, opacity.reshape(-1),
                                     f_dc.reshape(-1, 3), f_rest if M > 1 else None, 0, M, None, None, pose, 1)
         ctx.st = st

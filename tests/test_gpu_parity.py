@@ -331,7 +331,7 @@ def test_per_point_adam_vs_reference_golden(golden_dir):
         opt.step()
         for mine, ref in ((a, f"a{it}"), (opt.state[a]["exp_avg"], f"am{it}"), (opt.state[a]["exp_avg_sq"], f"av{it}"),
                           (b, f"b{it}"), (opt.state[b]["exp_avg"], f"bm{it}"), (opt.state[b]["exp_avg_sq"], f"bv{it}")):
-            np.testing.assert_allclose(mine.detach().cpu().numpy(), z[ref], rtol=2e-6, atol=1e-12, err_msg=ref)
+            np.testing.assert_allclose(mine.detach().cpu().numpy(), z[ref], rtol=3e-6, atol=1e-7, err_msg=ref)
         assert opt.state[a]["step"] == it + 1
     # error behaviour mirrors the reference
     with pytest.raises(ValueError):
@@ -366,7 +366,7 @@ def test_per_point_adam_large_unaligned():
             O.per_point_adam_step(ref[i], gr[i], ms[i], vs[i], it + 1, 1e-3 if i == 0 else 2e-3,
                                   per_point_lr=ppl if i == 0 else None)
     for i in range(len(ps)):
-        np.testing.assert_allclose(params[i].detach().cpu().numpy(), ref[i].numpy(), rtol=3e-6, atol=1e-9)
+        np.testing.assert_allclose(params[i].detach().cpu().numpy(), ref[i].numpy(), rtol=3e-6, atol=1e-7)
 
 
 # ----------------------------------------------------------------------------------------------

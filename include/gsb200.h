@@ -166,6 +166,8 @@ enum {
 GSB_API void gsb_profile_enable(int on);
 GSB_API int gsb_profile_collect(double* ms_sum, int64_t* count, int n_ids);
 GSB_API uint64_t gsb_launch_count(void);
+/* Tuning switches: "blend_version" = 1 (one pixel per lane) | 2 (two pixels per lane, packed f32x2; default). */
+GSB_API int gsb_set_option(const char* name, int value);
 
 GSB_API const char* gsb_last_error(void);
 GSB_API int gsb_abi_version(void);

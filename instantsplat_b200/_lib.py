@@ -54,7 +54,7 @@ ADAM_MAX_TENSORS = 8
 EXPORTS = ("gsb_geom_bytes", "gsb_binning_bytes", "gsb_image_bytes", "gsb_preprocess", "gsb_render",
            "gsb_backward", "gsb_mark_visible", "gsb_ssim_forward", "gsb_ssim_backward",
            "gsb_loss_forward", "gsb_loss_backward", "gsb_adam_step", "gsb_last_error",
-           "gsb_abi_version", "gsb_profile_enable", "gsb_profile_collect", "gsb_launch_count")
+           "gsb_abi_version", "gsb_profile_enable", "gsb_profile_collect", "gsb_launch_count", "gsb_set_option")
 KERNEL_IDS = ("preprocess", "sort_depth", "scan", "duplicate", "sort_tile", "gather", "blend_fwd", "blend_bwd",
               "preprocess_bwd", "loss_fwd", "loss_bwd", "adam")
 
@@ -107,6 +107,8 @@ def lib() -> ctypes.CDLL:
     L.gsb_profile_collect.argtypes = [vp, vp, ctypes.c_int]
     L.gsb_profile_collect.restype = ctypes.c_int
     L.gsb_launch_count.restype = ctypes.c_uint64
+    L.gsb_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    L.gsb_set_option.restype = ctypes.c_int
     for f in ("gsb_preprocess", "gsb_render", "gsb_backward", "gsb_mark_visible", "gsb_ssim_forward",
               "gsb_ssim_backward", "gsb_loss_forward", "gsb_loss_backward", "gsb_adam_step"):
         getattr(L, f).restype = ctypes.c_int

@@ -148,8 +148,9 @@ GS_HD void sh_to_rgb(int D, const float* sh_dc, const float* sh_rest, float x, f
   }
 }
 
-// Backward of sh_to_rgb: writes d/dsh (dc: 3, rest: 3*(K-1) for the K active coeffs; caller
-// zero-fills inactive ones) and returns dL/ddir.
+// Backward of sh_to_rgb: writes d/dsh (dc: 3, rest: 3*(K-1) for the K active coeffs; inactive
+// ones are left untouched) and returns dL/ddir.  ALIAS-SAFE: d_rest may be the same memory as
+// sh_rest (each channel's coefficients are read into registers before that channel is written).
 GS_HD void sh_to_rgb_bwd(int D, const float* sh_rest, float x, float y, float z, const float* dL,
                          float* d_dc, float* d_rest, float* ddir) {
   float gx = 0.f, gy = 0.f, gz = 0.f;
@@ -160,34 +161,34 @@ GS_HD void sh_to_rgb_bwd(int D, const float* sh_rest, float x, float y, float z,
     if (D > 0) {
       const float* s = sh_rest + ch;
       float* o = d_rest + ch;
-      o[0] = -SH_C1 * y * g; o[3] = SH_C1 * z * g; o[6] = -SH_C1 * x * g;
-      float dx = -SH_C1 * s[6], dy = -SH_C1 * s[0], dz = SH_C1 * s[3];
+      float c1 = s[0], c2 = s[3], c3 = s[6];
+      float dx = -SH_C1 * c3, dy = -SH_C1 * c1, dz = SH_C1 * c2;
       if (D > 1) {
-        o[9] = SH_C2_0 * xy * g; o[12] = SH_C2_1 * yz * g; o[15] = SH_C2_2 * (2.f * zz - xx - yy) * g;
-        o[18] = SH_C2_3 * xz * g; o[21] = SH_C2_4 * (xx - yy) * g;
-        dx += SH_C2_0 * y * s[9] + SH_C2_2 * (-2.f * x) * s[15] + SH_C2_3 * z * s[18] +
-              SH_C2_4 * 2.f * x * s[21];
-        dy += SH_C2_0 * x * s[9] + SH_C2_1 * z * s[12] + SH_C2_2 * (-2.f * y) * s[15] +
-              SH_C2_4 * (-2.f * y) * s[21];
-        dz += SH_C2_1 * y * s[12] + SH_C2_2 * 4.f * z * s[15] + SH_C2_3 * x * s[18];
+        float c4 = s[9], c5 = s[12], c6 = s[15], c7 = s[18], c8 = s[21];
+        dx += SH_C2_0 * y * c4 + SH_C2_2 * (-2.f * x) * c6 + SH_C2_3 * z * c7 + SH_C2_4 * 2.f * x * c8;
+        dy += SH_C2_0 * x * c4 + SH_C2_1 * z * c5 + SH_C2_2 * (-2.f * y) * c6 + SH_C2_4 * (-2.f * y) * c8;
+        dz += SH_C2_1 * y * c5 + SH_C2_2 * 4.f * z * c6 + SH_C2_3 * x * c7;
         if (D > 2) {
+          float c9 = s[24], c10 = s[27], c11 = s[30], c12 = s[33], c13 = s[36], c14 = s[39], c15 = s[42];
+          dx += SH_C3_0 * c9 * 6.f * xy + SH_C3_1 * c10 * yz + SH_C3_2 * c11 * (-2.f * xy) +
+                SH_C3_3 * c12 * (-6.f * xz) + SH_C3_4 * c13 * (4.f * zz - 3.f * xx - yy) +
+                SH_C3_5 * c14 * 2.f * xz + SH_C3_6 * c15 * (3.f * xx - 3.f * yy);
+          dy += SH_C3_0 * c9 * (3.f * xx - 3.f * yy) + SH_C3_1 * c10 * xz +
+                SH_C3_2 * c11 * (4.f * zz - xx - 3.f * yy) + SH_C3_3 * c12 * (-6.f * yz) +
+                SH_C3_4 * c13 * (-2.f * xy) + SH_C3_5 * c14 * (-2.f * yz) + SH_C3_6 * c15 * (-6.f * xy);
+          dz += SH_C3_1 * c10 * xy + SH_C3_2 * c11 * 8.f * yz +
+                SH_C3_3 * c12 * (6.f * zz - 3.f * xx - 3.f * yy) + SH_C3_4 * c13 * 8.f * xz +
+                SH_C3_5 * c14 * (xx - yy);
           o[24] = SH_C3_0 * y * (3.f * xx - yy) * g; o[27] = SH_C3_1 * xy * z * g;
           o[30] = SH_C3_2 * y * (4.f * zz - xx - yy) * g;
           o[33] = SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy) * g;
           o[36] = SH_C3_4 * x * (4.f * zz - xx - yy) * g; o[39] = SH_C3_5 * z * (xx - yy) * g;
           o[42] = SH_C3_6 * x * (xx - 3.f * yy) * g;
-          dx += SH_C3_0 * s[24] * 6.f * xy + SH_C3_1 * s[27] * yz + SH_C3_2 * s[30] * (-2.f * xy) +
-                SH_C3_3 * s[33] * (-6.f * xz) + SH_C3_4 * s[36] * (4.f * zz - 3.f * xx - yy) +
-                SH_C3_5 * s[39] * 2.f * xz + SH_C3_6 * s[42] * (3.f * xx - 3.f * yy);
-          dy += SH_C3_0 * s[24] * (3.f * xx - 3.f * yy) + SH_C3_1 * s[27] * xz +
-                SH_C3_2 * s[30] * (4.f * zz - xx - 3.f * yy) + SH_C3_3 * s[33] * (-6.f * yz) +
-                SH_C3_4 * s[36] * (-2.f * xy) + SH_C3_5 * s[39] * (-2.f * yz) +
-                SH_C3_6 * s[42] * (-6.f * xy);
-          dz += SH_C3_1 * s[27] * xy + SH_C3_2 * s[30] * 8.f * yz +
-                SH_C3_3 * s[33] * (6.f * zz - 3.f * xx - 3.f * yy) + SH_C3_4 * s[36] * 8.f * xz +
-                SH_C3_5 * s[39] * (xx - yy);
         }
+        o[9] = SH_C2_0 * xy * g; o[12] = SH_C2_1 * yz * g; o[15] = SH_C2_2 * (2.f * zz - xx - yy) * g;
+        o[18] = SH_C2_3 * xz * g; o[21] = SH_C2_4 * (xx - yy) * g;
       }
+      o[0] = -SH_C1 * y * g; o[3] = SH_C1 * z * g; o[6] = -SH_C1 * x * g;
       gx += dx * g; gy += dy * g; gz += dz * g;
     }
   }

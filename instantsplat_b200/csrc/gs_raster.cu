@@ -28,6 +28,9 @@
 
 using namespace gsb;
 
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
 // ------------------------------------------------------------------------------------------
 // error handling
 // ------------------------------------------------------------------------------------------
@@ -87,6 +90,13 @@ extern "C" GSB_API int gsb_profile_collect(double* ms_sum, int64_t* count, int n
   return GSB_OK;
 }
 extern "C" GSB_API uint64_t gsb_launch_count(void) { return g_launches; }
+static int g_blend_version = 2;
+// option "blend_version": 1 = one pixel per lane (8 warps / tile), 2 = two pixels per lane + packed f32x2
+extern "C" GSB_API int gsb_set_option(const char* name, int value) {
+  if (name && strcmp(name, "blend_version") == 0 && (value == 1 || value == 2)) { g_blend_version = value; return GSB_OK; }
+  snprintf(g_err, sizeof(g_err), "gsb_set_option: unknown option or bad value");
+  return GSB_ERR_INVALID;
+}
 struct ProfScope {
   int slot; cudaStream_t st;
   ProfScope(int id, cudaStream_t s, int launches = 1) : st(s) { gsb_count_launch(launches); slot = gsb_prof_begin(id, s); }
@@ -478,24 +488,42 @@ k_ranges_gather(uint32_t R, GeomView gv, BinView bv) {
   if (e == 0 || bv.keys_s[e - 1] != tile) bv.ranges[tile].x = e;
   if (e == R - 1 || bv.keys_s[e + 1] != tile) bv.ranges[tile].y = e + 1;
   float4 a = gv.xyAB[i], b = gv.Codq[i], c = gv.rgbr[i];
-  bv.s0[e] = a;
-  bv.s1[e] = make_float4(b.x, b.y, b.w, __uint_as_float(i));
+  // conic pre-scaled into the log2 domain: power*log2(e) = A' dx^2 + B' dx dy + C' dy^2
+  bv.s0[e] = make_float4(a.x, a.y, -0.5f * kLog2e * a.z, -kLog2e * a.w);
+  bv.s1[e] = make_float4(-0.5f * kLog2e * b.x, b.y, 0.5f * kLog2e * b.w, __uint_as_float(i));
   bv.s2[e] = make_float4(c.x, c.y, c.z, 0.f);
 }
 
 // ------------------------------------------------------------------------------------------
 // blend
 // ------------------------------------------------------------------------------------------
-struct PairEval { float dx, dy, power, G, alpha; };
+struct PairEval { float dx, dy, power, G, alpha; };   // power is in the log2 domain (power * log2 e)
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ PairEval pair_eval(const float4& e0, const float4& e1, float fx, float fy) {
   PairEval r;
   r.dx = e0.x - fx;
   r.dy = e0.y - fy;
-  r.power = -0.5f * (e0.z * r.dx * r.dx + e1.x * r.dy * r.dy) - e0.w * r.dx * r.dy;
-  r.G = __expf(r.power);
+  r.power = e0.z * r.dx * r.dx + (e0.w * r.dx + e1.x * r.dy) * r.dy;
+  r.G = ex2_approx(r.power);   // MUFU.EX2 directly (valid pairs have power >= -8)
   r.alpha = fminf(0.99f, e1.y * r.G);
   return r;
+}
+
+// cull test on a slab entry: q' = -(A'dx^2 + B'dxdy + C'dy^2) = q * log2(e)/2 against qthr' = qthr * log2(e)/2
+__device__ __forceinline__ bool slab_may_contribute(const float4& e0, const float4& e1, float rx0, float ry0,
+                                                    float rx1, float ry1) {
+  return rect_may_contribute(e0.x, e0.y, -e0.z, -0.5f * e0.w, -e1.x, e1.z, rx0, ry0, rx1, ry1);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -533,7 +561,7 @@ k_blend_fwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, con
         bool hit = false;
         if (j < cnt) {
           float4 e0 = sm0[j], e1 = sm1[j];
-          hit = rect_may_contribute(e0.x, e0.y, e0.z, e0.w, e1.x, e1.z, rx0, ry0, rx1, ry1);
+          hit = slab_may_contribute(e0, e1, rx0, ry0, rx1, ry1);
         }
         unsigned mask = __ballot_sync(0xffffffffu, hit);
         while (mask) {
@@ -565,6 +593,10 @@ k_blend_fwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, con
     out_color[hw + pix] = Cg + T * bg[1];
     out_color[2 * hw + pix] = Cb + T * bg[2];
   }
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // Reduce 9 per-lane values over the warp with 14 shuffles.  On return, lane l with (l & 3) == 0
@@ -659,7 +691,7 @@ k_blend_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, con
         bool hit = false;
         if (j < cnt && base + j < wmax) {
           float4 e0 = sm0[j], e1 = sm1[j];
-          hit = rect_may_contribute(e0.x, e0.y, e0.z, e0.w, e1.x, e1.z, rx0, ry0, rx1, ry1);
+          hit = slab_may_contribute(e0, e1, rx0, ry0, rx1, ry1);
         }
         unsigned mask = __ballot_sync(0xffffffffu, hit);
         while (mask) {
@@ -675,7 +707,8 @@ k_blend_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, con
           for (int u = 0; u < 9; ++u) v[u] = 0.f;
           if (valid) {
             const float4 c = sm2[b + k];
-            T = T / (1.f - pe.alpha);
+            const float inv1ma = rcp_approx(1.f - pe.alpha);      // 1-alpha in [0.01, 1]
+            T = T * inv1ma;
             const float dchannel_dcolor = pe.alpha * T;
             acc_r = last_alpha * last_r + (1.f - last_alpha) * acc_r; last_r = c.x;
             acc_g = last_alpha * last_g + (1.f - last_alpha) * acc_g; last_g = c.y;
@@ -683,11 +716,12 @@ k_blend_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, con
             float dL_dalpha = (c.x - acc_r) * dLr + (c.y - acc_g) * dLg + (c.z - acc_b) * dLb;
             dL_dalpha *= T;
             last_alpha = pe.alpha;
-            dL_dalpha += (-T_final / (1.f - pe.alpha)) * bg_dot;
+            dL_dalpha -= T_final * inv1ma * bg_dot;
             const float dL_dG = e1.y * dL_dalpha;
             const float gdx = pe.G * pe.dx, gdy = pe.G * pe.dy;
-            v[0] = dL_dG * (-gdx * e0.z - gdy * e0.w);
-            v[1] = dL_dG * (-gdy * e1.x - gdx * e0.w);
+            // -A = 2 ln2 A', -B = ln2 B', -C = 2 ln2 C'
+            v[0] = dL_dG * kLn2 * (2.f * gdx * e0.z + gdy * e0.w);
+            v[1] = dL_dG * kLn2 * (2.f * gdy * e1.x + gdx * e0.w);
             v[2] = -0.5f * gdx * pe.dx * dL_dG;
             v[3] = -gdx * pe.dy * dL_dG;
             v[4] = -0.5f * gdy * pe.dy * dL_dG;
@@ -697,8 +731,248 @@ k_blend_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, con
             v[8] = dchannel_dcolor * dLb;
           }
           warp_reduce9(v, lane);
+          // lane 4i holds total i (i < 8): pull 4 consecutive totals into lanes 0 and 16 and issue two
+          // 128-bit reductions (REDG.E.ADD.F32x4) + one scalar instead of nine scalar atomics
+          const float a1 = __shfl_down_sync(0xffffffffu, v[0], 4);
+          const float a2 = __shfl_down_sync(0xffffffffu, v[0], 8);
+          const float a3 = __shfl_down_sync(0xffffffffu, v[0], 12);
           float* dst = dacc + (size_t)__float_as_uint(e1.w) * 12;
-          if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), v[0]);
+          if ((lane & 15) == 0) red_add_v4(dst + (lane >> 2), v[0], a1, a2, a3);
+          if (lane == 1) atomicAdd(dst + 8, v[8]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// blend v2: 4 warps per tile, each warp owns an 8x8 block = two 8x4 halves; every lane carries TWO
+// pixels (x, y) and (x, y+4) that share dx, and the per-pair arithmetic is issued as packed
+// FFMA2/FMUL2/FADD2 (Blackwell f32x2), so one instruction stream serves 64 (pixel, Gaussian) pairs.
+// The sub-tile cull is evaluated per half and the loop runs over the union of the two masks.
+// ------------------------------------------------------------------------------------------
+constexpr int kThreads2 = 128;
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+
+__global__ void __launch_bounds__(kThreads2)
+k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
+             const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+             float* __restrict__ out_color, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+  __shared__ float4 sm0[kChunk], sm1[kChunk], sm2[kChunk];
+  const int tile = blockIdx.x;
+  const int tx = tile % gx, ty = tile / gx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sx0 = tx * kBlock + (warp & 1) * 8, sy0 = ty * kBlock + (warp >> 1) * 8;
+  const int px = sx0 + (lane & 7), pyA = sy0 + (lane >> 3), pyB = pyA + 4;
+  const bool inA = px < W && pyA < H, inB = px < W && pyB < H;
+  const float fx = (float)px;
+  const float2 fy = f2((float)pyA, (float)pyB);
+  const float rx0 = (float)sx0, rx1 = (float)min(sx0 + 7, W - 1);
+  const float ryA0 = (float)sy0, ryA1 = (float)min(sy0 + 3, H - 1);
+  const float ryB0 = (float)(sy0 + 4), ryB1 = (float)min(sy0 + 7, H - 1);
+  const uint2 rg = ranges[tile];
+  const int n = (int)(rg.y - rg.x);
+  float2 T = f2(1.f, 1.f), Cr = f2(0.f, 0.f), Cg = f2(0.f, 0.f), Cb = f2(0.f, 0.f);
+  uint32_t lastA = 0, lastB = 0;
+  bool doneA = !inA, doneB = !inB;
+  bool wdoneA = !(sx0 < W && sy0 < H), wdoneB = !(sx0 < W && sy0 + 4 < H);
+  for (int base = 0; base < n; base += kChunk) {
+    const int cnt = min(kChunk, n - base);
+    for (int k = threadIdx.x; k < cnt; k += kThreads2) {
+      size_t e = (size_t)rg.x + base + k;
+      sm0[k] = s0[e];
+      sm1[k] = s1[e];
+      sm2[k] = s2[e];
+    }
+    __syncthreads();
+    if (!(wdoneA && wdoneB)) {
+      for (int b = 0; b < cnt; b += 32) {
+        const int j = b + lane;
+        bool hitA = false, hitB = false;
+        if (j < cnt) {
+          const float4 e0 = sm0[j], e1 = sm1[j];
+          if (!wdoneA) hitA = slab_may_contribute(e0, e1, rx0, ryA0, rx1, ryA1);
+          if (!wdoneB) hitB = slab_may_contribute(e0, e1, rx0, ryB0, rx1, ryB1);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, hitA || hitB);
+        while (mask) {
+          const int k = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float4 e0 = sm0[b + k], e1 = sm1[b + k], c = sm2[b + k];
+          const float dx = e0.x - fx;
+          const float2 dy = f2(e0.y - fy.x, e0.y - fy.y);
+          const float c1 = e0.w * dx, c0 = e0.z * dx * dx;
+          // power' = c0 + dy * (c1 + C' * dy)
+          const float2 pw = __ffma2_rn(dy, __ffma2_rn(f2s(e1.x), dy, f2s(c1)), f2s(c0));
+          const float2 G = f2(ex2_approx(pw.x), ex2_approx(pw.y));
+          float2 al = __fmul2_rn(f2s(e1.y), G);
+          al.x = fminf(0.99f, al.x); al.y = fminf(0.99f, al.y);
+          bool vA = !doneA && pw.x <= 0.f && al.x >= kAlphaMin;
+          bool vB = !doneB && pw.y <= 0.f && al.y >= kAlphaMin;
+          const float2 tT = __fmul2_rn(T, __ffma2_rn(al, f2s(-1.f), f2s(1.f)));
+          if (vA && tT.x < kTEps) { doneA = true; vA = false; }
+          if (vB && tT.y < kTEps) { doneB = true; vB = false; }
+          float2 w = __fmul2_rn(al, T);
+          w.x = vA ? w.x : 0.f; w.y = vB ? w.y : 0.f;
+          Cr = __ffma2_rn(f2s(c.x), w, Cr);
+          Cg = __ffma2_rn(f2s(c.y), w, Cg);
+          Cb = __ffma2_rn(f2s(c.z), w, Cb);
+          const uint32_t pos = (uint32_t)(base + b + k + 1);
+          T.x = vA ? tT.x : T.x; T.y = vB ? tT.y : T.y;
+          lastA = vA ? pos : lastA; lastB = vB ? pos : lastB;
+        }
+        wdoneA = __all_sync(0xffffffffu, doneA);
+        wdoneB = __all_sync(0xffffffffu, doneB);
+        if (wdoneA && wdoneB) break;
+      }
+    }
+    if (__syncthreads_and(wdoneA && wdoneB)) break;
+  }
+  const size_t hw = (size_t)W * H;
+  const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+  if (inA) {
+    size_t pix = (size_t)pyA * W + px;
+    final_T[pix] = T.x; n_contrib[pix] = lastA;
+    out_color[pix] = Cr.x + T.x * b0; out_color[hw + pix] = Cg.x + T.x * b1; out_color[2 * hw + pix] = Cb.x + T.x * b2;
+  }
+  if (inB) {
+    size_t pix = (size_t)pyB * W + px;
+    final_T[pix] = T.y; n_contrib[pix] = lastB;
+    out_color[pix] = Cr.y + T.y * b0; out_color[hw + pix] = Cg.y + T.y * b1; out_color[2 * hw + pix] = Cb.y + T.y * b2;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads2)
+k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
+             const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+             const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
+             const float* __restrict__ dL_dpix, float* __restrict__ dacc) {
+  __shared__ float4 sm0[kChunk], sm1[kChunk], sm2[kChunk];
+  __shared__ int s_bmax;
+  const int tile = blockIdx.x;
+  const int tx = tile % gx, ty = tile / gx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sx0 = tx * kBlock + (warp & 1) * 8, sy0 = ty * kBlock + (warp >> 1) * 8;
+  const int px = sx0 + (lane & 7), pyA = sy0 + (lane >> 3), pyB = pyA + 4;
+  const bool inA = px < W && pyA < H, inB = px < W && pyB < H;
+  const float fx = (float)px;
+  const float2 fy = f2((float)pyA, (float)pyB);
+  const float rx0 = (float)sx0, rx1 = (float)min(sx0 + 7, W - 1);
+  const float ryA0 = (float)sy0, ryA1 = (float)min(sy0 + 3, H - 1);
+  const float ryB0 = (float)(sy0 + 4), ryB1 = (float)min(sy0 + 7, H - 1);
+  const uint2 rg = ranges[tile];
+  const size_t hw = (size_t)W * H;
+  const size_t pixA = (size_t)pyA * W + px, pixB = (size_t)pyB * W + px;
+  const float2 T_final = f2(inA ? final_T[pixA] : 0.f, inB ? final_T[pixB] : 0.f);
+  const int lcA = inA ? (int)n_contrib[pixA] : 0, lcB = inB ? (int)n_contrib[pixB] : 0;
+  float2 dLr = f2(0.f, 0.f), dLg = f2(0.f, 0.f), dLb = f2(0.f, 0.f);
+  if (inA) { dLr.x = dL_dpix[pixA]; dLg.x = dL_dpix[hw + pixA]; dLb.x = dL_dpix[2 * hw + pixA]; }
+  if (inB) { dLr.y = dL_dpix[pixB]; dLg.y = dL_dpix[hw + pixB]; dLb.y = dL_dpix[2 * hw + pixB]; }
+  const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+  const float2 tf_bg = __fmul2_rn(T_final, f2(b0 * dLr.x + b1 * dLg.x + b2 * dLb.x, b0 * dLr.y + b1 * dLg.y + b2 * dLb.y));
+  int wmaxA = lcA, wmaxB = lcB;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wmaxA = max(wmaxA, __shfl_xor_sync(0xffffffffu, wmaxA, o));
+    wmaxB = max(wmaxB, __shfl_xor_sync(0xffffffffu, wmaxB, o));
+  }
+  const int wmax = max(wmaxA, wmaxB);
+  if (threadIdx.x == 0) s_bmax = 0;
+  __syncthreads();
+  if (lane == 0) atomicMax(&s_bmax, wmax);
+  __syncthreads();
+  const int bmax = s_bmax;
+  float2 T = T_final;
+  float2 acc_r = f2(0.f, 0.f), acc_g = f2(0.f, 0.f), acc_b = f2(0.f, 0.f), last_alpha = f2(0.f, 0.f);
+  float2 last_r = f2(0.f, 0.f), last_g = f2(0.f, 0.f), last_b = f2(0.f, 0.f);
+  const int nchunks = (bmax + kChunk - 1) / kChunk;
+  for (int ch = nchunks - 1; ch >= 0; --ch) {
+    const int base = ch * kChunk;
+    const int cnt = min(kChunk, bmax - base);
+    for (int k = threadIdx.x; k < cnt; k += kThreads2) {
+      size_t e = (size_t)rg.x + base + k;
+      sm0[k] = s0[e];
+      sm1[k] = s1[e];
+      sm2[k] = s2[e];
+    }
+    __syncthreads();
+    if (base < wmax) {
+      for (int b = (cnt - 1) & ~31; b >= 0; b -= 32) {
+        if (base + b >= wmax) continue;
+        const int j = b + lane;
+        bool hit = false;
+        if (j < cnt) {
+          const float4 e0 = sm0[j], e1 = sm1[j];
+          if (base + j < wmaxA) hit = slab_may_contribute(e0, e1, rx0, ryA0, rx1, ryA1);
+          if (!hit && base + j < wmaxB) hit = slab_may_contribute(e0, e1, rx0, ryB0, rx1, ryB1);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+          const int k = 31 - __clz(mask);
+          mask &= ~(1u << k);
+          const int pos = base + b + k;
+          const float4 e0 = sm0[b + k], e1 = sm1[b + k];
+          const float dx = e0.x - fx;
+          const float2 dy = f2(e0.y - fy.x, e0.y - fy.y);
+          const float c1 = e0.w * dx, c0 = e0.z * dx * dx;
+          const float2 pw = __ffma2_rn(dy, __ffma2_rn(f2s(e1.x), dy, f2s(c1)), f2s(c0));
+          const float2 G = f2(ex2_approx(pw.x), ex2_approx(pw.y));
+          float2 al = __fmul2_rn(f2s(e1.y), G);
+          al.x = fminf(0.99f, al.x); al.y = fminf(0.99f, al.y);
+          const bool vA = inA && pos < lcA && pw.x <= 0.f && al.x >= kAlphaMin;
+          const bool vB = inB && pos < lcB && pw.y <= 0.f && al.y >= kAlphaMin;
+          if (!__any_sync(0xffffffffu, vA || vB)) continue;
+          const float4 c = sm2[b + k];
+          // masked alpha: an invalid pixel behaves as alpha = 0 (T, accumulators and gradients unchanged)
+          const float2 am = f2(vA ? al.x : 0.f, vB ? al.y : 0.f);
+          const float2 one_m = __ffma2_rn(am, f2s(-1.f), f2s(1.f));
+          const float2 inv = f2(rcp_approx(one_m.x), rcp_approx(one_m.y));
+          T = __fmul2_rn(T, inv);
+          const float2 dcol = __fmul2_rn(am, T);                 // dchannel/dcolor = alpha * T
+          // accum_rec = last_alpha * last_color + (1 - last_alpha) * accum_rec   (only advances on valid)
+          const float2 la = last_alpha, oml = __ffma2_rn(la, f2s(-1.f), f2s(1.f));
+          float2 nr = __ffma2_rn(la, last_r, __fmul2_rn(oml, acc_r));
+          float2 ng = __ffma2_rn(la, last_g, __fmul2_rn(oml, acc_g));
+          float2 nb = __ffma2_rn(la, last_b, __fmul2_rn(oml, acc_b));
+          acc_r.x = vA ? nr.x : acc_r.x; acc_r.y = vB ? nr.y : acc_r.y;
+          acc_g.x = vA ? ng.x : acc_g.x; acc_g.y = vB ? ng.y : acc_g.y;
+          acc_b.x = vA ? nb.x : acc_b.x; acc_b.y = vB ? nb.y : acc_b.y;
+          last_r.x = vA ? c.x : last_r.x; last_r.y = vB ? c.x : last_r.y;
+          last_g.x = vA ? c.y : last_g.x; last_g.y = vB ? c.y : last_g.y;
+          last_b.x = vA ? c.z : last_b.x; last_b.y = vB ? c.z : last_b.y;
+          last_alpha.x = vA ? al.x : last_alpha.x; last_alpha.y = vB ? al.y : last_alpha.y;
+          // dL/dalpha = T * sum_ch (c - accum_rec) dL_ch  -  T_final/(1-alpha) * bg.dL
+          float2 da = __fmul2_rn(__fadd2_rn(f2s(c.x), f2(-acc_r.x, -acc_r.y)), dLr);
+          da = __ffma2_rn(__fadd2_rn(f2s(c.y), f2(-acc_g.x, -acc_g.y)), dLg, da);
+          da = __ffma2_rn(__fadd2_rn(f2s(c.z), f2(-acc_b.x, -acc_b.y)), dLb, da);
+          da = __fmul2_rn(da, T);
+          da = __ffma2_rn(f2(-tf_bg.x, -tf_bg.y), inv, da);
+          da.x = vA ? da.x : 0.f; da.y = vB ? da.y : 0.f;
+          const float2 dG = __fmul2_rn(f2s(e1.y), da);           // dL/dG = opacity * dL/dalpha
+          const float2 gdG = __fmul2_rn(G, dG);                  // G * dL/dG
+          const float2 gy = __fmul2_rn(gdG, dy);                 // G dL/dG dy
+          const float gxs = (gdG.x + gdG.y) * dx;                // sum over the two pixels of G dL/dG dx
+          const float gys = gy.x + gy.y;
+          float v[9];
+          v[0] = kLn2 * (2.f * gxs * e0.z + gys * e0.w);
+          v[1] = kLn2 * (2.f * gys * e1.x + gxs * e0.w);
+          v[2] = -0.5f * gxs * dx;
+          v[3] = -dx * gys;
+          v[4] = -0.5f * (gy.x * dy.x + gy.y * dy.y);
+          v[5] = G.x * da.x + G.y * da.y;
+          const float dcs_r = dcol.x * dLr.x + dcol.y * dLr.y;
+          v[6] = dcs_r;
+          v[7] = dcol.x * dLg.x + dcol.y * dLg.y;
+          v[8] = dcol.x * dLb.x + dcol.y * dLb.y;
+          warp_reduce9(v, lane);
+          const float a1 = __shfl_down_sync(0xffffffffu, v[0], 4);
+          const float a2 = __shfl_down_sync(0xffffffffu, v[0], 8);
+          const float a3 = __shfl_down_sync(0xffffffffu, v[0], 12);
+          float* dst = dacc + (size_t)__float_as_uint(e1.w) * 12;
+          if ((lane & 15) == 0) red_add_v4(dst + (lane >> 2), v[0], a1, a2, a3);
           if (lane == 1) atomicAdd(dst + 8, v[8]);
         }
       }
@@ -715,7 +989,7 @@ struct OutPtrs {
   float* dsh_dc; float* dsh_rest; float* dcolors; float* dcov3D;
 };
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_preprocess_bwd(InPtrs in, GeomView gv, const int* __restrict__ radii_unused, OutPtrs out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CamConst* cam = reinterpret_cast<CamConst*>(smem_raw);
@@ -741,16 +1015,16 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int* __restrict__ radii_unused, O
 #pragma unroll
   for (int k = 0; k < 16; ++k) pa[k] = 0.f;
   GaussGrad gg;
-  float ddc[3] = {0.f, 0.f, 0.f};
-  float drest[45];
-#pragma unroll
-  for (int k = 0; k < 45; ++k) drest[k] = 0.f;
   gg.dm[0] = gg.dm[1] = gg.dm[2] = 0.f; gg.dsc[0] = gg.dsc[1] = gg.dsc[2] = 0.f;
   gg.dq[0] = gg.dq[1] = gg.dq[2] = gg.dq[3] = 0.f; gg.dop = 0.f;
   gg.dmeans2D[0] = gg.dmeans2D[1] = 0.f;
 #pragma unroll
   for (int k = 0; k < 6; ++k) gg.dcov3D[k] = 0.f;
   gg.dcolor[0] = gg.dcolor[1] = gg.dcolor[2] = 0.f;
+  // Every thread touches only its own shared-memory rows from here on (no barrier needed until the
+  // cooperative stores): the SH gradient is written IN PLACE over the staged SH row.
+  float* row = sm_sh + t * kRowPad;
+  bool has = false;
   if (t < nv) {
     float4 d0 = gv.dacc[3 * (size_t)i], d1 = gv.dacc[3 * (size_t)i + 1], d2 = gv.dacc[3 * (size_t)i + 2];
     float ds[9] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x};
@@ -764,21 +1038,17 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int* __restrict__ radii_unused, O
       project_geometry(*cam, g, in.cov3D ? in.cov3D + (size_t)6 * i : nullptr, p);
       if (p.visible) {
         p.clamped = gv.clamped[i];
-        project_bwd(*cam, g, p, sm_sh + t * kRowPad + 3, use_sh, in.cov3D != nullptr, ds, gg, ddc, drest, pa);
+        project_bwd(*cam, g, p, row + 3, use_sh, in.cov3D != nullptr, ds, gg, row, row + 3, pa);
+        has = use_sh;
       }
     }
-  }
-  __syncthreads();   // everyone is done reading sm_sh / sm_geo
-  if (t < nv) {
+    const int first_zero = has ? 3 * (D + 1) * (D + 1) : 0;     // inactive coefficients get zero gradient
+    for (int k = first_zero; k < 48; ++k) row[k] = 0.f;
     float* r = sm_geo + t * kGeoPad;
     r[0] = gg.dm[0]; r[1] = gg.dm[1]; r[2] = gg.dm[2];
     r[3] = gg.dsc[0]; r[4] = gg.dsc[1]; r[5] = gg.dsc[2];
     r[6] = gg.dq[0]; r[7] = gg.dq[1]; r[8] = gg.dq[2]; r[9] = gg.dq[3];
     r[10] = gg.dop;
-    float* s = sm_sh + t * kRowPad;
-    s[0] = ddc[0]; s[1] = ddc[1]; s[2] = ddc[2];
-#pragma unroll
-    for (int k = 0; k < 45; ++k) s[3 + k] = drest[k];
     if (out.dmeans2D) {
       out.dmeans2D[3 * (size_t)i] = gg.dmeans2D[0];
       out.dmeans2D[3 * (size_t)i + 1] = gg.dmeans2D[1];
@@ -957,8 +1227,12 @@ extern "C" GSB_API int gsb_render(const GsbCamera* cam, int32_t P, void* geom, v
       k_ranges_gather<<<(unsigned)((R + kThreads - 1) / kThreads), kThreads, 0, st>>>((uint32_t)R, gv, bv); }
   }
   { ProfScope ps(GSB_K_BLEND_FWD, st);
-    k_blend_fwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, out_color,
-                                              iv.final_T, iv.n_contrib); }
+    if (g_blend_version == 2)
+      k_blend_fwd2<<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, out_color,
+                                                  iv.final_T, iv.n_contrib);
+    else
+      k_blend_fwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, out_color,
+                                                iv.final_T, iv.n_contrib); }
   GSB_CUDA(cudaGetLastError());
   return GSB_OK;
 }
@@ -985,8 +1259,12 @@ extern "C" GSB_API int gsb_backward(const GsbCamera* cam, const GsbGaussians* g,
   GSB_CUDA(cudaMemsetAsync(gv.dacc, 0, (size_t)P * 48, st));
   if (R > 0) {
     ProfScope ps(GSB_K_BLEND_BWD, st);
-    k_blend_bwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, iv.final_T,
-                                              iv.n_contrib, dL_dout, (float*)gv.dacc);
+    if (g_blend_version == 2)
+      k_blend_bwd2<<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, iv.final_T,
+                                                  iv.n_contrib, dL_dout, (float*)gv.dacc);
+    else
+      k_blend_bwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, iv.final_T,
+                                                iv.n_contrib, dL_dout, (float*)gv.dacc);
   }
   OutPtrs out;
   out.dmeans = grads->dL_dmeans3D; out.dmeans2D = grads->dL_dmeans2D; out.dscales = grads->dL_dscales;

@@ -175,6 +175,27 @@ def test_exact_cull_is_lossless():
         assert rel_err(a_g[k], b_g[k]) < 1e-4, k
 
 
+def test_blend_kernel_versions_agree():
+    """v1 (one pixel per lane) and v2 (two pixels per lane, packed f32x2) blend kernels."""
+    import instantsplat_b200 as I
+    L = I.lib()
+    sc = surface_scene(40_000, 3, 300, 200, seed=17, sh_degree=2)
+    bg = torch.tensor([0.1, 0.0, 0.2])
+    gt = torch.rand(3, sc.height, sc.width, generator=torch.Generator().manual_seed(3))
+    try:
+        assert L.gsb_set_option(b"blend_version", 1) == 0
+        a_img, a_r, a_loss, a_g = cuda_run(sc, 2, bg, gt)
+        assert L.gsb_set_option(b"blend_version", 2) == 0
+        b_img, b_r, b_loss, b_g = cuda_run(sc, 2, bg, gt)
+    finally:
+        L.gsb_set_option(b"blend_version", 2)
+    assert L.gsb_set_option(b"blend_version", 7) != 0 and L.gsb_set_option(b"nope", 1) != 0
+    assert torch.equal(a_r, b_r)
+    assert float((a_img - b_img).abs().max()) < 2e-6
+    for k in NAMES + ("pose", "means2D"):
+        assert rel_err(b_g[k], a_g[k]) < 2e-4, k
+
+
 def test_generic_boundary_b2_nonidentity_view_packed_sh():
     """GaussianRasterizer called the vanilla-3DGS way (real view matrix, activated inputs, packed SHs)."""
     import instantsplat_b200 as I

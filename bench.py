@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json configs index (2 = headline)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink P (debug only; invalidates the number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="fused_p2p", choices=["allreduce", "fused_p2p"],
+                    help="multi-GPU gradient exchange: NCCL all-reduce + Adam, or the fused P2P "
+                         "reduce-scatter->Adam->all-gather kernel (default)")
     ap.add_argument("--cpu-budget-s", type=float, default=45.0)
     return ap.parse_args()
 
@@ -166,7 +169,7 @@ def cpu_arm(sc, steps, warmup, budget_s):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     from instantsplat_b200.scenes import make_config
     sc = make_config(args.config, args.scale)
     r = cpu_arm(sc, args.steps, args.warmup, budget_s=150.0)
@@ -179,7 +182,7 @@ def run_reference(args):
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference CUDA path (diff-gaussian-rasterization / fused-ssim) is an empty submodule in "
                     "/root/reference: this arm is the CPU oracle port of the same path"}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 # ----------------------------------------------------------------------------------------------
@@ -205,7 +208,7 @@ def run_b200(args):
     del tgt
     torch.cuda.empty_cache()
     gt_host = gt_dev.cpu().pin_memory()
-    tr = I.JointTrainer(sc, dev, gt_images=gt_dev, world_size=world, rank=rank)
+    tr = I.JointTrainer(sc, dev, gt_images=gt_dev, world_size=world, rank=rank, exchange=args.exchange)
     stage = torch.empty_like(gt_dev[0])
     loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
 
@@ -263,7 +266,7 @@ def run_b200(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        return None
     views = K * world
     value = views / (ms_dev / 1e3)
     e2e_value = views / (ms_e2e / 1e3)
@@ -308,7 +311,7 @@ def run_b200(args):
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.config, sc), "views_per_step": world,
-                   "parallelism": f"view-sharded dp{world}", "P": sc.P, "R_mean": tr.last_R,
+                   "parallelism": f"view-sharded dp{world}", "exchange": tr.exchange if world > 1 else "none", "P": sc.P, "R_mean": tr.last_R,
                    "l2": "working set (params+grads+moments 944 MB at 1M) exceeds the 126 MB L2; no explicit flush",
                    "iteration": "one view: render fwd + L1/DSSIM + bwd + per-point Adam (+ all-reduce if N>1)"},
         "render_mpix_per_s_fwd_bwd": sc.width * sc.height / (t_render * 1e-3) / 1e6,
@@ -318,14 +321,30 @@ def run_b200(args):
         "gpu_launches": launches, "gpu_launches_note": "libgsb200.so kernels only (cub sort/scan launches excluded)",
         "kernels": kernels, "roofline": roof, "clocks": clocks, "cpu_baseline": cpu_base, "impl": "b200",
     }
-    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return line
+
+
+class _QuietStdout:
+    """Libraries (NCCL's version banner, torchrun notices) must not pollute stdout: the contract is ONE JSON
+    line.  Route fd 1 to stderr for the duration of the run and restore it for the final print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_b200(a)
+    with _QuietStdout():
+        line = run_reference(a) if a.impl == "reference" else run_b200(a)
+    if line is not None:
+        print(json.dumps(line), flush=True)

@@ -156,6 +156,35 @@ typedef struct GsbAdamTensor {
 /* flags: [n] uint32 scratch (device); gate g.norm()>0 per tensor is evaluated on the device. */
 GSB_API int gsb_adam_step(int32_t n, const GsbAdamTensor* tensors_host, uint32_t* flags, gsb_stream_t stream);
 
+/* flags[k] = (tensor k's scaled gradient has a non-zero element); the gate half of gsb_adam_step, exposed so
+ * the multi-GPU path can all-reduce the flags before the fused exchange kernel. */
+GSB_API int gsb_adam_gate(int32_t n, const GsbAdamTensor* tensors_host, uint32_t* flags, gsb_stream_t stream);
+
+/* ---- multi-GPU: fused reduce-scatter -> per-point Adam -> all-gather over NVLink peer memory ----------
+ * (new functionality; the NCCL all-reduce + gsb_adam_step pair is the baseline it
+ * replaces).  Peer-visible buffers are cudaMalloc'ed here and shared between the per-GPU processes with
+ * CUDA IPC handles (64 bytes). */
+GSB_API int gsb_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+GSB_API int gsb_ipc_open(const unsigned char* handle64, void** dev_ptr);
+GSB_API int gsb_ipc_close(void* dev_ptr);
+GSB_API int gsb_ipc_free(void* dev_ptr);
+
+typedef struct GsbShardPiece { /* (one tensor's segment) intersected with (this rank's shard) */
+  int64_t begin, end;          /* flat-buffer element range, multiples of 4 */
+  int64_t seg_begin;           /* where the tensor's segment starts in the flat buffer */
+  const float* per_point_lr;   /* [rows] of the whole tensor, or NULL */
+  int32_t row_len;
+  int32_t flag_index;          /* which gate flag applies */
+  double step_size, beta1, beta2, eps;
+} GsbShardPiece;
+
+/* peer_grads / peer_params: host arrays of `world` device pointers to every rank's flat gradient / parameter
+ * buffer (own rank included).  exp_avg / exp_avg_sq: this rank's shard only, indexed by (element - shard_begin). */
+GSB_API int gsb_fused_rs_adam_ag(int32_t world, int32_t rank, const float* const* peer_grads,
+                                 float* const* peer_params, float* exp_avg_shard, float* exp_avg_sq_shard,
+                                 int64_t shard_begin, int32_t n_pieces, const GsbShardPiece* pieces,
+                                 const uint32_t* flags, float grad_scale, gsb_stream_t stream);
+
 /* Optional instrumentation (bench.py): per-kernel CUDA-event timing on the launching stream and a
  * count of this library's own kernel launches (cub launches are not counted). */
 enum {
@@ -166,7 +195,8 @@ enum {
 GSB_API void gsb_profile_enable(int on);
 GSB_API int gsb_profile_collect(double* ms_sum, int64_t* count, int n_ids);
 GSB_API uint64_t gsb_launch_count(void);
-/* Tuning switches: "blend_version" = 1 (one pixel per lane) | 2 (two pixels per lane, packed f32x2; default). */
+/* Tuning switches: "blend_version" = 1 (one pixel per lane) | 2 (two pixels per lane, packed f32x2; default);
+ * "stage_bulk" = 1 (slab chunks staged with cp.async.bulk/TMA + mbarrier, double buffered; default) | 0. */
 GSB_API int gsb_set_option(const char* name, int value);
 
 GSB_API const char* gsb_last_error(void);

@@ -50,11 +50,19 @@ class GsbAdamTensor(ctypes.Structure):
                 ("eps", ctypes.c_double), ("weight_decay", ctypes.c_double)]
 
 
+class GsbShardPiece(ctypes.Structure):
+    _fields_ = [("begin", ctypes.c_int64), ("end", ctypes.c_int64), ("seg_begin", ctypes.c_int64),
+                ("per_point_lr", ctypes.c_void_p), ("row_len", ctypes.c_int32), ("flag_index", ctypes.c_int32),
+                ("step_size", ctypes.c_double), ("beta1", ctypes.c_double), ("beta2", ctypes.c_double),
+                ("eps", ctypes.c_double)]
+
+
 ADAM_MAX_TENSORS = 8
 EXPORTS = ("gsb_geom_bytes", "gsb_binning_bytes", "gsb_image_bytes", "gsb_preprocess", "gsb_render",
            "gsb_backward", "gsb_mark_visible", "gsb_ssim_forward", "gsb_ssim_backward",
            "gsb_loss_forward", "gsb_loss_backward", "gsb_adam_step", "gsb_last_error",
-           "gsb_abi_version", "gsb_profile_enable", "gsb_profile_collect", "gsb_launch_count", "gsb_set_option")
+           "gsb_abi_version", "gsb_profile_enable", "gsb_profile_collect", "gsb_launch_count", "gsb_set_option", "gsb_adam_gate",
+           "gsb_ipc_alloc", "gsb_ipc_open", "gsb_ipc_close", "gsb_ipc_free", "gsb_fused_rs_adam_ag")
 KERNEL_IDS = ("preprocess", "sort_depth", "scan", "duplicate", "sort_tile", "gather", "blend_fwd", "blend_bwd",
               "preprocess_bwd", "loss_fwd", "loss_bwd", "adam")
 
@@ -109,6 +117,16 @@ def lib() -> ctypes.CDLL:
     L.gsb_launch_count.restype = ctypes.c_uint64
     L.gsb_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
     L.gsb_set_option.restype = ctypes.c_int
+    L.gsb_adam_gate.argtypes = [i32, ctypes.POINTER(GsbAdamTensor), vp, vp]
+    L.gsb_ipc_alloc.argtypes = [sz, ctypes.POINTER(vp), ctypes.c_char_p]
+    L.gsb_ipc_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.gsb_ipc_close.argtypes = [vp]
+    L.gsb_ipc_free.argtypes = [vp]
+    L.gsb_fused_rs_adam_ag.argtypes = [i32, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp, i64, i32,
+                                       ctypes.POINTER(GsbShardPiece), vp, ctypes.c_float, vp]
+    for f in ("gsb_adam_gate", "gsb_ipc_alloc", "gsb_ipc_open", "gsb_ipc_close", "gsb_ipc_free",
+              "gsb_fused_rs_adam_ag"):
+        getattr(L, f).restype = ctypes.c_int
     for f in ("gsb_preprocess", "gsb_render", "gsb_backward", "gsb_mark_visible", "gsb_ssim_forward",
               "gsb_ssim_backward", "gsb_loss_forward", "gsb_loss_backward", "gsb_adam_step"):
         getattr(L, f).restype = ctypes.c_int

@@ -118,20 +118,13 @@ __global__ void __launch_bounds__(kAT) k_adam(AdamArgs a, const unsigned int* __
 
 }  // namespace
 
-extern "C" GSB_API int gsb_adam_step(int32_t n, const GsbAdamTensor* ts, uint32_t* flags, gsb_stream_t stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
-  if (n < 0 || n > GSB_ADAM_MAX_TENSORS || (n > 0 && (!ts || !flags))) {
-    gsb_set_error("gsb_adam_step: bad argument");
-    return GSB_ERR_INVALID;
-  }
-  if (n == 0) return GSB_OK;
-  AdamArgs a;
+static int build_args(int32_t n, const GsbAdamTensor* ts, AdamArgs& a, unsigned int& nb) {
   a.n = n;
-  unsigned int nb = 0;
+  nb = 0;
   for (int i = 0; i < n; ++i) {
     const GsbAdamTensor& s = ts[i];
     if (!s.param || !s.grad || !s.exp_avg || !s.exp_avg_sq || s.numel < 0 || s.row_len <= 0) {
-      gsb_set_error("gsb_adam_step: null tensor / bad shape");
+      gsb_set_error("gsb_adam: null tensor / bad shape");
       return GSB_ERR_INVALID;
     }
     AdamT& t = a.t[i];
@@ -146,6 +139,48 @@ extern "C" GSB_API int gsb_adam_step(int32_t n, const GsbAdamTensor* ts, uint32_
     nb += t.nblocks;
   }
   for (int i = n; i < GSB_ADAM_MAX_TENSORS; ++i) { a.t[i] = a.t[0]; a.t[i].first_block = 0xffffffffu; a.t[i].nblocks = 0; }
+  return GSB_OK;
+}
+
+static int finish(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return GSB_OK;
+  char buf[256];
+  snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  gsb_set_error(buf);
+  return GSB_ERR_CUDA;
+}
+
+extern "C" GSB_API int gsb_adam_gate(int32_t n, const GsbAdamTensor* ts, uint32_t* flags, gsb_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n < 0 || n > GSB_ADAM_MAX_TENSORS || (n > 0 && (!ts || !flags))) {
+    gsb_set_error("gsb_adam_gate: bad argument");
+    return GSB_ERR_INVALID;
+  }
+  if (n == 0) return GSB_OK;
+  AdamArgs a;
+  unsigned int nb;
+  int rc = build_args(n, ts, a, nb);
+  if (rc) return rc;
+  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, st);
+  if (e == cudaSuccess && nb > 0) {
+    gsb_count_launch(1);
+    k_adam_gate<<<nb, kAT, 0, st>>>(a, flags);
+    e = cudaGetLastError();
+  }
+  return finish(e, "gsb_adam_gate");
+}
+
+extern "C" GSB_API int gsb_adam_step(int32_t n, const GsbAdamTensor* ts, uint32_t* flags, gsb_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n < 0 || n > GSB_ADAM_MAX_TENSORS || (n > 0 && (!ts || !flags))) {
+    gsb_set_error("gsb_adam_step: bad argument");
+    return GSB_ERR_INVALID;
+  }
+  if (n == 0) return GSB_OK;
+  AdamArgs a;
+  unsigned int nb;
+  int rc = build_args(n, ts, a, nb);
+  if (rc) return rc;
   cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, st);
   if (e == cudaSuccess && nb > 0) {
     gsb_count_launch(2);
@@ -155,11 +190,5 @@ extern "C" GSB_API int gsb_adam_step(int32_t n, const GsbAdamTensor* ts, uint32_
     gsb_prof_end(slot, st);
     e = cudaGetLastError();
   }
-  if (e != cudaSuccess) {
-    char buf[256];
-    snprintf(buf, sizeof(buf), "gsb_adam_step: %s", cudaGetErrorString(e));
-    gsb_set_error(buf);
-    return GSB_ERR_CUDA;
-  }
-  return GSB_OK;
+  return finish(e, "gsb_adam_step");
 }

@@ -1,0 +1,215 @@
+// Fused reduce-scatter -> per-point Adam -> all-gather over NVLink peer memory (sm_100a).
+//
+// Multi-GPU exchange of the view-sharded optimisation loop: every rank
+// holds a full replica of the flat parameter buffer and has just written its view's gradients into
+// its flat gradient buffer.  Rank r owns the r-th contiguous shard of the flat index space.  ONE
+// kernel per rank then, for each 128-bit group of its shard:
+//     g   = sum over ranks of peer_grads[rank][i]          (P2P loads over NVLink, fixed order)
+//     m,v = Adam moment update (local, shard-sized)         (scene/per_point_adam.py:66-73)
+//     p   = p - step * lr_i * m / (sqrt(v) + eps)           (:76-98)
+//     peer_params[rank][i] = p   for every rank             (P2P stores over NVLink)
+// i.e. the reduce-scatter, the optimizer and the all-gather of the "NCCL all-reduce + Adam"
+// baseline in one pass: gradients cross the links once, parameters once, Adam touches 1/G of the
+// elements per GPU, and the NCCL ring/tree launch latencies disappear.  The caller brackets it with
+// two tiny NCCL collectives (flag/pose-gradient all-reduce before, a barrier after) that double as
+// the cross-GPU barriers.
+//
+// Buffers that peers touch are allocated here with cudaMalloc and shared with CUDA IPC
+// (cudaIpcGetMemHandle / cudaIpcOpenMemHandle) because each GPU is driven by its own process.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gsb200.h"
+
+void gsb_set_error(const char* s);
+void gsb_count_launch(int n);
+int gsb_prof_begin(int id, cudaStream_t st);
+void gsb_prof_end(int slot, cudaStream_t st);
+
+namespace {
+
+constexpr int kMaxWorld = 8;
+constexpr int kMaxPieces = 12;
+
+struct Piece {
+  long long begin, end, seg_begin;   // flat-buffer element indices; begin/end multiples of 4
+  const float* ppl;
+  int row_len, flag_index;
+  float step, b1, omb1, b2, omb2, eps;
+  unsigned int first_block, nblocks;
+};
+struct FusedArgs {
+  int world, rank, n_pieces;
+  long long shard_begin;
+  float gscale;
+  const float* grads[kMaxWorld];
+  float* params[kMaxWorld];
+  float* m;
+  float* v;
+  Piece pc[kMaxPieces];
+};
+
+constexpr int kFT = 256;
+constexpr int kVecPerThread = 2;
+constexpr int kElemsPerBlock = kFT * kVecPerThread * 4;   // 2048
+
+__device__ __forceinline__ float4 ld_peer(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_peer(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void adam1(const Piece& t, bool gate, float lr_mul, float& p, float g, float& m, float& v) {
+  if (gate) {
+    m = __fadd_rn(__fmul_rn(m, t.b1), __fmul_rn(g, t.omb1));
+    v = __fadd_rn(__fmul_rn(v, t.b2), __fmul_rn(__fmul_rn(t.omb2, g), g));
+  }
+  float denom = __fadd_rn(__fsqrt_rn(v), t.eps);
+  p = __fadd_rn(p, __fmul_rn(-(t.step * lr_mul), __fdiv_rn(m, denom)));
+}
+
+template <int WORLD>
+__global__ void __launch_bounds__(kFT) k_fused_rs_adam_ag(FusedArgs a, const unsigned int* __restrict__ flags) {
+  int k = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxPieces; ++i)
+    if (i < a.n_pieces && blockIdx.x >= a.pc[i].first_block) k = i;
+  const Piece& t = a.pc[k];
+  const bool gate = flags[t.flag_index] != 0;
+  const long long base = t.begin + (long long)(blockIdx.x - t.first_block) * kElemsPerBlock;
+#pragma unroll
+  for (int u = 0; u < kVecPerThread; ++u) {
+    const long long e = base + ((long long)u * kFT + threadIdx.x) * 4;
+    if (e >= t.end) continue;
+    float4 g[WORLD];
+#pragma unroll
+    for (int r = 0; r < WORLD; ++r) g[r] = ld_peer(a.grads[r] + e);      // all loads in flight together
+    float4 s = g[0];
+#pragma unroll
+    for (int r = 1; r < WORLD; ++r) { s.x += g[r].x; s.y += g[r].y; s.z += g[r].z; s.w += g[r].w; }
+    s.x *= a.gscale; s.y *= a.gscale; s.z *= a.gscale; s.w *= a.gscale;
+    const long long le = e - a.shard_begin;
+    float4 p = *reinterpret_cast<const float4*>(a.params[a.rank] + e);
+    float4 m = *reinterpret_cast<float4*>(a.m + le);
+    float4 v = *reinterpret_cast<float4*>(a.v + le);
+    float l0 = 1.f, l1 = 1.f, l2 = 1.f, l3 = 1.f;
+    if (t.ppl) {
+      const long long q = e - t.seg_begin;
+      l0 = __ldg(t.ppl + q / t.row_len); l1 = __ldg(t.ppl + (q + 1) / t.row_len);
+      l2 = __ldg(t.ppl + (q + 2) / t.row_len); l3 = __ldg(t.ppl + (q + 3) / t.row_len);
+    }
+    adam1(t, gate, l0, p.x, s.x, m.x, v.x);
+    adam1(t, gate, l1, p.y, s.y, m.y, v.y);
+    adam1(t, gate, l2, p.z, s.z, m.z, v.z);
+    adam1(t, gate, l3, p.w, s.w, m.w, v.w);
+    *reinterpret_cast<float4*>(a.m + le) = m;
+    *reinterpret_cast<float4*>(a.v + le) = v;
+#pragma unroll
+    for (int r = 0; r < WORLD; ++r) st_peer(a.params[r] + e, p);
+  }
+}
+
+int fail(cudaError_t e, const char* what) {
+  char buf[256];
+  snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  gsb_set_error(buf);
+  return GSB_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" GSB_API int gsb_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  if (!dev_ptr || !handle64 || bytes == 0) { gsb_set_error("gsb_ipc_alloc: bad argument"); return GSB_ERR_INVALID; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaError_t e = cudaMalloc(dev_ptr, bytes);
+  if (e != cudaSuccess) return fail(e, "cudaMalloc");
+  e = cudaMemset(*dev_ptr, 0, bytes);
+  if (e != cudaSuccess) return fail(e, "cudaMemset");
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, *dev_ptr);
+  if (e != cudaSuccess) return fail(e, "cudaIpcGetMemHandle");
+  memcpy(handle64, &h, 64);
+  return GSB_OK;
+}
+
+extern "C" GSB_API int gsb_ipc_open(const unsigned char* handle64, void** dev_ptr) {
+  if (!dev_ptr || !handle64) { gsb_set_error("gsb_ipc_open: bad argument"); return GSB_ERR_INVALID; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(e, "cudaIpcOpenMemHandle");
+  return GSB_OK;
+}
+
+extern "C" GSB_API int gsb_ipc_close(void* dev_ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+  return e == cudaSuccess ? GSB_OK : fail(e, "cudaIpcCloseMemHandle");
+}
+
+extern "C" GSB_API int gsb_ipc_free(void* dev_ptr) {
+  cudaError_t e = cudaFree(dev_ptr);
+  return e == cudaSuccess ? GSB_OK : fail(e, "cudaFree");
+}
+
+extern "C" GSB_API int gsb_fused_rs_adam_ag(int32_t world, int32_t rank, const float* const* peer_grads,
+                                            float* const* peer_params, float* exp_avg_shard, float* exp_avg_sq_shard,
+                                            int64_t shard_begin, int32_t n_pieces, const GsbShardPiece* pieces,
+                                            const uint32_t* flags, float grad_scale, gsb_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || !peer_grads || !peer_params || !exp_avg_shard ||
+      !exp_avg_sq_shard || n_pieces < 0 || n_pieces > kMaxPieces || (n_pieces > 0 && !pieces) || !flags ||
+      (shard_begin & 3)) {
+    gsb_set_error("gsb_fused_rs_adam_ag: bad argument");
+    return GSB_ERR_INVALID;
+  }
+  FusedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.world = world; a.rank = rank; a.n_pieces = n_pieces; a.shard_begin = shard_begin; a.gscale = grad_scale;
+  a.m = exp_avg_shard; a.v = exp_avg_sq_shard;
+  for (int r = 0; r < world; ++r) {
+    if (!peer_grads[r] || !peer_params[r] || (((uintptr_t)peer_grads[r] | (uintptr_t)peer_params[r]) & 15)) {
+      gsb_set_error("gsb_fused_rs_adam_ag: null / misaligned peer pointer");
+      return GSB_ERR_INVALID;
+    }
+    a.grads[r] = peer_grads[r]; a.params[r] = peer_params[r];
+  }
+  unsigned int nb = 0;
+  for (int i = 0; i < n_pieces; ++i) {
+    const GsbShardPiece& s = pieces[i];
+    if (s.begin < shard_begin || s.end < s.begin || (s.begin & 3) || (s.end & 3) || s.row_len <= 0 ||
+        s.flag_index < 0 || s.flag_index >= GSB_ADAM_MAX_TENSORS) {
+      gsb_set_error("gsb_fused_rs_adam_ag: bad piece (ranges must be 4-float aligned)");
+      return GSB_ERR_INVALID;
+    }
+    Piece& t = a.pc[i];
+    t.begin = s.begin; t.end = s.end; t.seg_begin = s.seg_begin; t.ppl = s.per_point_lr;
+    t.row_len = s.row_len; t.flag_index = s.flag_index;
+    t.step = (float)s.step_size; t.b1 = (float)s.beta1; t.omb1 = (float)(1.0 - s.beta1);
+    t.b2 = (float)s.beta2; t.omb2 = (float)(1.0 - s.beta2); t.eps = (float)s.eps;
+    t.first_block = nb;
+    t.nblocks = (unsigned int)((s.end - s.begin + kElemsPerBlock - 1) / kElemsPerBlock);
+    nb += t.nblocks;
+  }
+  for (int i = n_pieces; i < kMaxPieces; ++i) a.pc[i].first_block = 0xffffffffu;
+  if (nb == 0) return GSB_OK;
+  gsb_count_launch(1);
+  int slot = gsb_prof_begin(GSB_K_ADAM, st);
+  switch (world) {
+    case 2: k_fused_rs_adam_ag<2><<<nb, kFT, 0, st>>>(a, flags); break;
+    case 3: k_fused_rs_adam_ag<3><<<nb, kFT, 0, st>>>(a, flags); break;
+    case 4: k_fused_rs_adam_ag<4><<<nb, kFT, 0, st>>>(a, flags); break;
+    case 5: k_fused_rs_adam_ag<5><<<nb, kFT, 0, st>>>(a, flags); break;
+    case 6: k_fused_rs_adam_ag<6><<<nb, kFT, 0, st>>>(a, flags); break;
+    case 7: k_fused_rs_adam_ag<7><<<nb, kFT, 0, st>>>(a, flags); break;
+    default: k_fused_rs_adam_ag<8><<<nb, kFT, 0, st>>>(a, flags); break;
+  }
+  gsb_prof_end(slot, st);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSB_OK : fail(e, "k_fused_rs_adam_ag");
+}

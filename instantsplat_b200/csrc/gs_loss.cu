@@ -6,10 +6,11 @@
 // padding, C1 = 0.01^2, C2 = 0.03^2, per-channel (depthwise), mean over all elements -- plus
 // l1_loss (/root/reference/utils/loss_utils.py:39-40) and the combine of train.py:176.
 //
-// One CTA = one 16x16 output tile of one channel: the (16+10)^2 halo of both images is staged in
-// shared memory once, the 11-tap window is applied separably (horizontal into shared memory,
-// vertical in registers), so HBM traffic is the compulsory read of the two images plus the three
-// partial-derivative maps written for the backward.
+// One CTA = one 32x16 output tile of one channel: the (32+10)x(16+10) halo of both images is staged
+// in shared memory once and the 11-tap window is applied separably with register tiling (4 outputs
+// per thread horizontally from 128-bit shared loads, 2 outputs per thread vertically), so HBM
+// traffic is the compulsory read of the two images plus the three partial-derivative maps written
+// for the backward.
 #include <cuda_runtime.h>
 #include <stdio.h>
 
@@ -22,9 +23,11 @@ void gsb_prof_end(int slot, cudaStream_t st);
 
 namespace {
 
-constexpr int TS = 16;          // tile edge
+constexpr int TW = 32, TH = 16;     // output tile per CTA
 constexpr int HALO = 5;
-constexpr int TE = TS + 2 * HALO;   // 26
+constexpr int EH = TH + 2 * HALO;   // 26 staged rows
+constexpr int EWP = 44;             // 42 staged columns padded to a multiple of 4 (128-bit shared loads)
+constexpr int HS = TW + 1;          // row stride of the horizontally filtered planes (conflict-free)
 constexpr float C1 = 0.01f * 0.01f;
 constexpr float C2 = 0.03f * 0.03f;
 
@@ -57,60 +60,97 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return r;   // valid in thread 0
 }
 
-// img planes [BC][H][W].  maps (optional) [3][BC][H][W].  sums[0] += sum|a-b| (if do_l1),
-// sums[1] += sum ssim.
+// Stage a (TH+10) x (TW+10) halo of one plane into shared memory (zero 'same' padding).
+__device__ __forceinline__ void stage_plane(float (*dst)[EWP], const float* __restrict__ src, int H, int W,
+                                            int x0, int y0) {
+  for (int k = threadIdx.x; k < EH * EWP; k += 256) {
+    int r = k / EWP, c = k - r * EWP;
+    int y = y0 + r - HALO, x = x0 + c - HALO;
+    bool in = (c < TW + 2 * HALO) && x >= 0 && x < W && y >= 0 && y < H;
+    dst[r][c] = in ? __ldg(src + (size_t)y * W + x) : 0.f;
+  }
+}
+
+// Register-tiled separable 11-tap filter.  Horizontal: thread -> (row, 4 adjacent columns), inputs
+// fetched with four 128-bit shared loads.  Vertical: thread -> (column, 2 adjacent rows).
+// img planes [BC][H][W].  maps (optional) [3][BC][H][W].  sums[0] += sum|a-b| (if do_l1), sums[1] += sum ssim.
 __global__ void __launch_bounds__(256)
 k_ssim_fwd(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
            double* __restrict__ sums, float* __restrict__ maps, size_t plane_total, int do_l1) {
-  __shared__ float sA[TE][TE + 1], sB[TE][TE + 1];
-  __shared__ float sH[5][TE][TS + 1];
+  __shared__ __align__(16) float sA[EH][EWP];
+  __shared__ __align__(16) float sB[EH][EWP];
+  __shared__ float sH[5][EH][HS];
   __shared__ float red[8];
   const int bc = blockIdx.z;
-  const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
-  const float* p1 = img1 + (size_t)bc * H * W;
-  const float* p2 = img2 + (size_t)bc * H * W;
-  for (int k = threadIdx.x; k < TE * TE; k += 256) {
-    int r = k / TE, c = k - r * TE;
-    int y = y0 + r - HALO, x = x0 + c - HALO;
-    bool in = (x >= 0 && x < W && y >= 0 && y < H);
-    sA[r][c] = in ? __ldg(p1 + (size_t)y * W + x) : 0.f;
-    sB[r][c] = in ? __ldg(p2 + (size_t)y * W + x) : 0.f;
-  }
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  stage_plane(sA, img1 + (size_t)bc * H * W, H, W, x0, y0);
+  stage_plane(sB, img2 + (size_t)bc * H * W, H, W, x0, y0);
   __syncthreads();
-  for (int k = threadIdx.x; k < TE * TS; k += 256) {
-    int r = k / TS, c = k - r * TS;
-    float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+  if (threadIdx.x < EH * (TW / 4)) {
+    const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
+    float a[16], b[16];
 #pragma unroll
-    for (int t = 0; t < 11; ++t) {
-      float w = c_win[t], a = sA[r][c + t], b = sB[r][c + t];
-      m1 += w * a; m2 += w * b; e11 += w * a * a; e22 += w * b * b; e12 += w * a * b;
+    for (int q = 0; q < 4; ++q) {
+      float4 va = *reinterpret_cast<const float4*>(&sA[r][c0 + 4 * q]);
+      float4 vb = *reinterpret_cast<const float4*>(&sB[r][c0 + 4 * q]);
+      a[4 * q] = va.x; a[4 * q + 1] = va.y; a[4 * q + 2] = va.z; a[4 * q + 3] = va.w;
+      b[4 * q] = vb.x; b[4 * q + 1] = vb.y; b[4 * q + 2] = vb.z; b[4 * q + 3] = vb.w;
     }
-    sH[0][r][c] = m1; sH[1][r][c] = m2; sH[2][r][c] = e11; sH[3][r][c] = e22; sH[4][r][c] = e12;
+    float acc[5][4];
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[q][o] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+      const float av = a[i], bv = b[i], aa = av * av, bb = bv * bv, ab = av * bv;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int t = i - o;
+        if (t >= 0 && t < 11) {
+          const float w = c_win[t];
+          acc[0][o] += w * av; acc[1][o] += w * bv; acc[2][o] += w * aa; acc[3][o] += w * bb; acc[4][o] += w * ab;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+#pragma unroll
+      for (int o = 0; o < 4; ++o) sH[q][r][c0 + o] = acc[q][o];
   }
   __syncthreads();
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int x = x0 + tx, y = y0 + ty;
+  const int tx = threadIdx.x & 31, ty = (threadIdx.x >> 5) * 2;
+  float v[5][12];
+#pragma unroll
+  for (int q = 0; q < 5; ++q)
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[q][i] = sH[q][ty + i][tx];
   float ssim_v = 0.f, l1_v = 0.f;
-  if (x < W && y < H) {
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    const int x = x0 + tx, y = y0 + ty + o;
     float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
 #pragma unroll
     for (int t = 0; t < 11; ++t) {
-      float w = c_win[t];
-      mu1 += w * sH[0][ty + t][tx]; mu2 += w * sH[1][ty + t][tx]; e11 += w * sH[2][ty + t][tx];
-      e22 += w * sH[3][ty + t][tx]; e12 += w * sH[4][ty + t][tx];
+      const float w = c_win[t];
+      mu1 += w * v[0][o + t]; mu2 += w * v[1][o + t]; e11 += w * v[2][o + t]; e22 += w * v[3][o + t];
+      e12 += w * v[4][o + t];
     }
-    float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
-    float s1 = e11 - mu1_sq, s2 = e22 - mu2_sq, s12 = e12 - mu12;
-    float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2, B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
-    float inv = 1.f / (B1 * B2);
-    ssim_v = A1 * A2 * inv;
-    if (maps) {
-      size_t o = (size_t)bc * H * W + (size_t)y * W + x;
-      maps[o] = 2.f * mu2 * (A2 - A1) * inv - ssim_v * 2.f * mu1 * (B2 - B1) * inv;   // d/dmu1
-      maps[plane_total + o] = -ssim_v / B2;                                        // d/dE[x^2]
-      maps[2 * plane_total + o] = 2.f * A1 * inv;                                  // d/dE[xy]
+    if (x < W && y < H) {
+      float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+      float s1 = e11 - mu1_sq, s2 = e22 - mu2_sq, s12 = e12 - mu12;
+      float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2, B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
+      float inv = 1.f / (B1 * B2);
+      float sv = A1 * A2 * inv;
+      ssim_v += sv;
+      if (maps) {
+        size_t off = (size_t)bc * H * W + (size_t)y * W + x;
+        maps[off] = 2.f * mu2 * (A2 - A1) * inv - sv * 2.f * mu1 * (B2 - B1) * inv;   // d/dmu1
+        maps[plane_total + off] = -sv / B2;                                       // d/dE[x^2]
+        maps[2 * plane_total + off] = 2.f * A1 * inv;                             // d/dE[xy]
+      }
+      if (do_l1) l1_v += fabsf(sA[ty + o + HALO][tx + HALO] - sB[ty + o + HALO][tx + HALO]);
     }
-    if (do_l1) l1_v = fabsf(sA[ty + HALO][tx + HALO] - sB[ty + HALO][tx + HALO]);
   }
   float s = block_sum(ssim_v, red);
   if (threadIdx.x == 0) atomicAdd(sums + 1, (double)s);
@@ -126,50 +166,64 @@ __global__ void __launch_bounds__(256)
 k_ssim_bwd(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
            const float* __restrict__ maps, size_t plane_total, float ssim_scale,
            const float* __restrict__ dyn_scale, float l1_scale, float* __restrict__ out) {
-  __shared__ float sM[3][TE][TE + 1];
-  __shared__ float sH[3][TE][TS + 1];
+  __shared__ __align__(16) float sM[3][EH][EWP];
+  __shared__ float sH[3][EH][HS];
   const int bc = blockIdx.z;
-  const int x0 = blockIdx.x * TS, y0 = blockIdx.y * TS;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const size_t pbase = (size_t)bc * H * W;
-  for (int k = threadIdx.x; k < TE * TE; k += 256) {
-    int r = k / TE, c = k - r * TE;
-    int y = y0 + r - HALO, x = x0 + c - HALO;
-    bool in = (x >= 0 && x < W && y >= 0 && y < H);
-    size_t o = pbase + (size_t)y * W + x;
-    sM[0][r][c] = in ? __ldg(maps + o) : 0.f;
-    sM[1][r][c] = in ? __ldg(maps + plane_total + o) : 0.f;
-    sM[2][r][c] = in ? __ldg(maps + 2 * plane_total + o) : 0.f;
+  stage_plane(sM[0], maps + pbase, H, W, x0, y0);
+  stage_plane(sM[1], maps + plane_total + pbase, H, W, x0, y0);
+  stage_plane(sM[2], maps + 2 * plane_total + pbase, H, W, x0, y0);
+  __syncthreads();
+  if (threadIdx.x < EH * (TW / 4)) {
+    const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      float a[16];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float4 va = *reinterpret_cast<const float4*>(&sM[q][r][c0 + 4 * u]);
+        a[4 * u] = va.x; a[4 * u + 1] = va.y; a[4 * u + 2] = va.z; a[4 * u + 3] = va.w;
+      }
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 14; ++i)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int t = i - o;
+          if (t >= 0 && t < 11) acc[o] += c_win[t] * a[i];
+        }
+#pragma unroll
+      for (int o = 0; o < 4; ++o) sH[q][r][c0 + o] = acc[o];
+    }
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < TE * TS; k += 256) {
-    int r = k / TS, c = k - r * TS;
+  const int tx = threadIdx.x & 31, ty = (threadIdx.x >> 5) * 2;
+  float v[3][12];
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[q][i] = sH[q][ty + i][tx];
+  const float sc = ssim_scale * (dyn_scale ? *dyn_scale : 1.f);
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    const int x = x0 + tx, y = y0 + ty + o;
     float a = 0.f, b = 0.f, d = 0.f;
 #pragma unroll
     for (int t = 0; t < 11; ++t) {
-      float w = c_win[t];
-      a += w * sM[0][r][c + t]; b += w * sM[1][r][c + t]; d += w * sM[2][r][c + t];
+      const float w = c_win[t];
+      a += w * v[0][o + t]; b += w * v[1][o + t]; d += w * v[2][o + t];
     }
-    sH[0][r][c] = a; sH[1][r][c] = b; sH[2][r][c] = d;
-  }
-  __syncthreads();
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int x = x0 + tx, y = y0 + ty;
-  if (x < W && y < H) {
-    float a = 0.f, b = 0.f, d = 0.f;
-#pragma unroll
-    for (int t = 0; t < 11; ++t) {
-      float w = c_win[t];
-      a += w * sH[0][ty + t][tx]; b += w * sH[1][ty + t][tx]; d += w * sH[2][ty + t][tx];
+    if (x < W && y < H) {
+      size_t off = pbase + (size_t)y * W + x;
+      float xv = img1[off], yv = img2[off];
+      float g = sc * (a + 2.f * xv * b + yv * d);
+      if (l1_scale != 0.f) {
+        float df = xv - yv;
+        g += l1_scale * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
+      }
+      out[off] = g;
     }
-    size_t o = pbase + (size_t)y * W + x;
-    float xv = img1[o], yv = img2[o];
-    float sc = ssim_scale * (dyn_scale ? *dyn_scale : 1.f);
-    float g = sc * (a + 2.f * xv * b + yv * d);
-    if (l1_scale != 0.f) {
-      float df = xv - yv;
-      g += l1_scale * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
-    }
-    out[o] = g;
   }
 }
 
@@ -187,7 +241,7 @@ extern "C" GSB_API int gsb_ssim_forward(int32_t BC, int32_t H, int32_t W, const 
                                 double* ssim_sum2, float* maps, gsb_stream_t stream) {
   if (BC <= 0 || H <= 0 || W <= 0 || !img1 || !img2 || !ssim_sum2) { gsb_set_error("gsb_ssim_forward: bad argument"); return GSB_ERR_INVALID; }
   if (ensure_window()) return check(cudaGetLastError(), "window upload");
-  dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS, BC);
+  dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, BC);
   gsb_count_launch(1);
   int slot = gsb_prof_begin(GSB_K_LOSS_FWD, (cudaStream_t)stream);
   k_ssim_fwd<<<grid, 256, 0, (cudaStream_t)stream>>>(H, W, img1, img2, ssim_sum2, maps, (size_t)BC * H * W, 0);
@@ -200,7 +254,7 @@ extern "C" GSB_API int gsb_ssim_backward(int32_t BC, int32_t H, int32_t W, const
                                  float* dL_dimg1, gsb_stream_t stream) {
   if (BC <= 0 || H <= 0 || W <= 0 || !img1 || !img2 || !maps || !dL_dimg1) { gsb_set_error("gsb_ssim_backward: bad argument"); return GSB_ERR_INVALID; }
   if (ensure_window()) return check(cudaGetLastError(), "window upload");
-  dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS, BC);
+  dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, BC);
   gsb_count_launch(1);
   int slot = gsb_prof_begin(GSB_K_LOSS_BWD, (cudaStream_t)stream);
   k_ssim_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(H, W, img1, img2, maps, (size_t)BC * H * W, scale_host,
@@ -213,7 +267,7 @@ extern "C" GSB_API int gsb_loss_forward(int32_t C, int32_t H, int32_t W, const f
                                 double* sums, float* maps, gsb_stream_t stream) {
   if (C <= 0 || H <= 0 || W <= 0 || !img || !gt || !sums || !maps) { gsb_set_error("gsb_loss_forward: bad argument"); return GSB_ERR_INVALID; }
   if (ensure_window()) return check(cudaGetLastError(), "window upload");
-  dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS, C);
+  dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, C);
   gsb_count_launch(1);
   int slot = gsb_prof_begin(GSB_K_LOSS_FWD, (cudaStream_t)stream);
   k_ssim_fwd<<<grid, 256, 0, (cudaStream_t)stream>>>(H, W, img, gt, sums, maps, (size_t)C * H * W, 1);
@@ -226,7 +280,7 @@ extern "C" GSB_API int gsb_loss_backward(int32_t C, int32_t H, int32_t W, const 
   if (C <= 0 || H <= 0 || W <= 0 || !img || !gt || !maps || !dL_dimg) { gsb_set_error("gsb_loss_backward: bad argument"); return GSB_ERR_INVALID; }
   if (ensure_window()) return check(cudaGetLastError(), "window upload");
   const double N = (double)C * H * W;
-  dim3 grid((W + TS - 1) / TS, (H + TS - 1) / TS, C);
+  dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, C);
   gsb_count_launch(1);
   int slot = gsb_prof_begin(GSB_K_LOSS_BWD, (cudaStream_t)stream);
   k_ssim_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(H, W, img, gt, maps, (size_t)C * H * W,

@@ -91,9 +91,11 @@ extern "C" GSB_API int gsb_profile_collect(double* ms_sum, int64_t* count, int n
 }
 extern "C" GSB_API uint64_t gsb_launch_count(void) { return g_launches; }
 static int g_blend_version = 2;
+static int g_stage_bulk = 1;   // 1: slabs staged with cp.async.bulk (TMA) + mbarrier, 0: cooperative loads
 // option "blend_version": 1 = one pixel per lane (8 warps / tile), 2 = two pixels per lane + packed f32x2
 extern "C" GSB_API int gsb_set_option(const char* name, int value) {
   if (name && strcmp(name, "blend_version") == 0 && (value == 1 || value == 2)) { g_blend_version = value; return GSB_OK; }
+  if (name && strcmp(name, "stage_bulk") == 0 && (value == 0 || value == 1)) { g_stage_bulk = value; return GSB_OK; }
   snprintf(g_err, sizeof(g_err), "gsb_set_option: unknown option or bad value");
   return GSB_ERR_INVALID;
 }
@@ -173,9 +175,10 @@ static GeomView geom_view(void* base, int P) {
   return v;
 }
 
+typedef uint16_t tkey_t;   // tile id: 16 bits cover 65535 tiles (a 4K frame has 32400)
 struct BinView {
-  uint32_t* keys;
-  uint32_t* keys_s;
+  tkey_t* keys;
+  tkey_t* keys_s;
   uint32_t* vals;
   uint32_t* vals_s;
   float4* s0;          // x, y, A, B
@@ -200,8 +203,8 @@ static BinView bin_view(void* base, int64_t R, int W, int H) {
   size_t Rp = (size_t)(R > 0 ? R : 1);
   int ntiles = ((W + kBlock - 1) / kBlock) * ((H + kBlock - 1) / kBlock);
   auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += align_up(bytes); return r; };
-  v.keys = (uint32_t*)take(Rp * 4);
-  v.keys_s = (uint32_t*)take(Rp * 4);
+  v.keys = (tkey_t*)take(Rp * sizeof(tkey_t));
+  v.keys_s = (tkey_t*)take(Rp * sizeof(tkey_t));
   v.vals = (uint32_t*)take(Rp * 4);
   v.vals_s = (uint32_t*)take(Rp * 4);
   v.s0 = (float4*)take(Rp * 16);
@@ -209,8 +212,9 @@ static BinView bin_view(void* base, int64_t R, int W, int H) {
   v.s2 = (float4*)take(Rp * 16);
   v.ranges = (uint2*)take((size_t)ntiles * 8);
   size_t a = 0;
-  uint32_t* k = nullptr;
-  cub::DeviceRadixSort::SortPairs(nullptr, a, k, k, k, k, (int)Rp, 0, tile_bits(ntiles));
+  tkey_t* k = nullptr;
+  uint32_t* vv = nullptr;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, k, k, vv, vv, (int)Rp, 0, tile_bits(ntiles));
   v.cub_bytes = a + 1024;
   v.cub_tmp = take(v.cub_bytes);
   v.total = off;
@@ -376,7 +380,7 @@ __device__ __forceinline__ void read_gauss(const float* sm_geo, int t, bool has_
 }
 
 __device__ __forceinline__ uint32_t count_or_emit_tiles(const Proj& p, float qthr, int W, int H, int gx,
-                                                        bool cull, uint32_t* keys, uint32_t* vals,
+                                                        bool cull, tkey_t* keys, uint32_t* vals,
                                                         uint32_t id) {
   uint32_t n = 0;
   for (int ty = p.ry0; ty < p.ry1; ++ty)
@@ -388,7 +392,7 @@ __device__ __forceinline__ uint32_t count_or_emit_tiles(const Proj& p, float qth
         keep = rect_may_contribute(p.x, p.y, p.A, p.B, p.C, qthr, x0, y0, x1, y1);
       }
       if (keep) {
-        if (keys) { keys[n] = (uint32_t)(ty * gx + tx); vals[n] = id; }
+        if (keys) { keys[n] = (tkey_t)(ty * gx + tx); vals[n] = id; }
         ++n;
       }
     }
@@ -754,14 +758,82 @@ k_blend_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, con
 // ------------------------------------------------------------------------------------------
 constexpr int kThreads2 = 128;
 
+// ------------------------------------------------------------------------------------------
+// TMA (bulk async copy) staging of the per-tile slabs: one elected thread arms an mbarrier with the
+// byte count and issues cp.async.bulk.shared.global for the three slab arrays of the NEXT chunk
+// while the CTA blends the current one (double buffered).  SASS: UBLKCP + SYNCS.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+struct SlabStage {
+  float4 s0[kChunk], s1[kChunk], s2[kChunk];
+};
+
+// Stage `cnt` slab entries starting at global entry `e0` into `dst`.  BULK: thread 0 issues three bulk copies
+// that complete on `bar`; otherwise all threads copy cooperatively (caller synchronises).
+template <bool BULK>
+__device__ __forceinline__ void stage_slab(SlabStage* dst, const float4* __restrict__ s0, const float4* __restrict__ s1,
+                                           const float4* __restrict__ s2, size_t e0, int cnt, uint64_t* bar,
+                                           int nthreads) {
+  if (BULK) {
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)cnt * 16u;
+      mbar_expect_tx(bar, 3u * bytes);
+      bulk_g2s(dst->s0, s0 + e0, bytes, bar);
+      bulk_g2s(dst->s1, s1 + e0, bytes, bar);
+      bulk_g2s(dst->s2, s2 + e0, bytes, bar);
+    }
+  } else {
+    for (int k = threadIdx.x; k < cnt; k += nthreads) {
+      dst->s0[k] = s0[e0 + k];
+      dst->s1[k] = s1[e0 + k];
+      dst->s2[k] = s2[e0 + k];
+    }
+  }
+}
+
+
+
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
 
-__global__ void __launch_bounds__(kThreads2)
+template <bool BULK>
+__global__ void __launch_bounds__(kThreads2, 7)
 k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
              const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
              float* __restrict__ out_color, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
-  __shared__ float4 sm0[kChunk], sm1[kChunk], sm2[kChunk];
+  __shared__ __align__(128) SlabStage stg[BULK ? 2 : 1];
+  __shared__ __align__(8) uint64_t bars[2];
+  if (BULK) {
+    if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+  }
   const int tile = blockIdx.x;
   const int tx = tile % gx, ty = tile / gx;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -779,15 +851,28 @@ k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
   uint32_t lastA = 0, lastB = 0;
   bool doneA = !inA, doneB = !inB;
   bool wdoneA = !(sx0 < W && sy0 < H), wdoneB = !(sx0 < W && sy0 + 4 < H);
-  for (int base = 0; base < n; base += kChunk) {
+  const int nch = (n + kChunk - 1) / kChunk;
+  if (BULK && nch > 0) stage_slab<true>(&stg[0], s0, s1, s2, (size_t)rg.x, min(kChunk, n), &bars[0], kThreads2);
+  int pending = -1;    // chunk whose bulk copy is in flight but has not been waited for
+  for (int ci = 0; ci < nch; ++ci) {
+    const int base = ci * kChunk;
     const int cnt = min(kChunk, n - base);
-    for (int k = threadIdx.x; k < cnt; k += kThreads2) {
-      size_t e = (size_t)rg.x + base + k;
-      sm0[k] = s0[e];
-      sm1[k] = s1[e];
-      sm2[k] = s2[e];
+    const SlabStage* cur = &stg[BULK ? (ci & 1) : 0];
+    if (BULK) {
+      pending = -1;
+      if (ci + 1 < nch) {     // prefetch the next chunk into the other stage (freed by the barrier below)
+        stage_slab<true>(&stg[(ci + 1) & 1], s0, s1, s2, (size_t)rg.x + base + kChunk, min(kChunk, n - base - kChunk),
+                         &bars[(ci + 1) & 1], kThreads2);
+        pending = ci + 1;
+      }
+      mbar_wait(&bars[ci & 1], (uint32_t)((ci >> 1) & 1));
+    } else {
+      stage_slab<false>(&stg[0], s0, s1, s2, (size_t)rg.x + base, cnt, nullptr, kThreads2);
+      __syncthreads();
     }
-    __syncthreads();
+    const float4* sm0 = cur->s0;
+    const float4* sm1 = cur->s1;
+    const float4* sm2 = cur->s2;
     if (!(wdoneA && wdoneB)) {
       for (int b = 0; b < cnt; b += 32) {
         const int j = b + lane;
@@ -830,7 +915,9 @@ k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
       }
     }
     if (__syncthreads_and(wdoneA && wdoneB)) break;
+    pending = -1;
   }
+  if (BULK && pending >= 0) mbar_wait(&bars[pending & 1], (uint32_t)((pending >> 1) & 1));   // never exit with a copy in flight
   const size_t hw = (size_t)W * H;
   const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
   if (inA) {
@@ -845,13 +932,16 @@ k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
   }
 }
 
-__global__ void __launch_bounds__(kThreads2)
+template <bool BULK>
+__global__ void __launch_bounds__(kThreads2, 6)
 k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
              const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
              const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
              const float* __restrict__ dL_dpix, float* __restrict__ dacc) {
-  __shared__ float4 sm0[kChunk], sm1[kChunk], sm2[kChunk];
+  __shared__ __align__(128) SlabStage stg[BULK ? 2 : 1];
+  __shared__ __align__(8) uint64_t bars[2];
   __shared__ int s_bmax;
+  if (BULK && threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
   const int tile = blockIdx.x;
   const int tx = tile % gx, ty = tile / gx;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -886,19 +976,29 @@ k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
   __syncthreads();
   const int bmax = s_bmax;
   float2 T = T_final;
-  float2 acc_r = f2(0.f, 0.f), acc_g = f2(0.f, 0.f), acc_b = f2(0.f, 0.f), last_alpha = f2(0.f, 0.f);
-  float2 last_r = f2(0.f, 0.f), last_g = f2(0.f, 0.f), last_b = f2(0.f, 0.f);
+  float2 acc_r = f2(0.f, 0.f), acc_g = f2(0.f, 0.f), acc_b = f2(0.f, 0.f);
   const int nchunks = (bmax + kChunk - 1) / kChunk;
-  for (int ch = nchunks - 1; ch >= 0; --ch) {
+  // chunks are visited back to front; it = 0 is the LAST chunk
+  if (BULK && nchunks > 0)
+    stage_slab<true>(&stg[0], s0, s1, s2, (size_t)rg.x + (size_t)(nchunks - 1) * kChunk,
+                     min(kChunk, bmax - (nchunks - 1) * kChunk), &bars[0], kThreads2);
+  for (int it = 0; it < nchunks; ++it) {
+    const int ch = nchunks - 1 - it;
     const int base = ch * kChunk;
     const int cnt = min(kChunk, bmax - base);
-    for (int k = threadIdx.x; k < cnt; k += kThreads2) {
-      size_t e = (size_t)rg.x + base + k;
-      sm0[k] = s0[e];
-      sm1[k] = s1[e];
-      sm2[k] = s2[e];
+    const SlabStage* cur = &stg[BULK ? (it & 1) : 0];
+    if (BULK) {
+      if (it + 1 < nchunks)
+        stage_slab<true>(&stg[(it + 1) & 1], s0, s1, s2, (size_t)rg.x + base - kChunk, kChunk, &bars[(it + 1) & 1],
+                         kThreads2);
+      mbar_wait(&bars[it & 1], (uint32_t)((it >> 1) & 1));
+    } else {
+      stage_slab<false>(&stg[0], s0, s1, s2, (size_t)rg.x + base, cnt, nullptr, kThreads2);
+      __syncthreads();
     }
-    __syncthreads();
+    const float4* sm0 = cur->s0;
+    const float4* sm1 = cur->s1;
+    const float4* sm2 = cur->s2;
     if (base < wmax) {
       for (int b = (cnt - 1) & ~31; b >= 0; b -= 32) {
         if (base + b >= wmax) continue;
@@ -926,31 +1026,24 @@ k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
           const bool vB = inB && pos < lcB && pw.y <= 0.f && al.y >= kAlphaMin;
           if (!__any_sync(0xffffffffu, vA || vB)) continue;
           const float4 c = sm2[b + k];
-          // masked alpha: an invalid pixel behaves as alpha = 0 (T, accumulators and gradients unchanged)
+          // masked alpha: an invalid pixel behaves as alpha = 0 (T, accumulator and gradients unchanged)
           const float2 am = f2(vA ? al.x : 0.f, vB ? al.y : 0.f);
           const float2 one_m = __ffma2_rn(am, f2s(-1.f), f2s(1.f));
           const float2 inv = f2(rcp_approx(one_m.x), rcp_approx(one_m.y));
           T = __fmul2_rn(T, inv);
           const float2 dcol = __fmul2_rn(am, T);                 // dchannel/dcolor = alpha * T
-          // accum_rec = last_alpha * last_color + (1 - last_alpha) * accum_rec   (only advances on valid)
-          const float2 la = last_alpha, oml = __ffma2_rn(la, f2s(-1.f), f2s(1.f));
-          float2 nr = __ffma2_rn(la, last_r, __fmul2_rn(oml, acc_r));
-          float2 ng = __ffma2_rn(la, last_g, __fmul2_rn(oml, acc_g));
-          float2 nb = __ffma2_rn(la, last_b, __fmul2_rn(oml, acc_b));
-          acc_r.x = vA ? nr.x : acc_r.x; acc_r.y = vB ? nr.y : acc_r.y;
-          acc_g.x = vA ? ng.x : acc_g.x; acc_g.y = vB ? ng.y : acc_g.y;
-          acc_b.x = vA ? nb.x : acc_b.x; acc_b.y = vB ? nb.y : acc_b.y;
-          last_r.x = vA ? c.x : last_r.x; last_r.y = vB ? c.x : last_r.y;
-          last_g.x = vA ? c.y : last_g.x; last_g.y = vB ? c.y : last_g.y;
-          last_b.x = vA ? c.z : last_b.x; last_b.y = vB ? c.z : last_b.y;
-          last_alpha.x = vA ? al.x : last_alpha.x; last_alpha.y = vB ? al.y : last_alpha.y;
-          // dL/dalpha = T * sum_ch (c - accum_rec) dL_ch  -  T_final/(1-alpha) * bg.dL
-          float2 da = __fmul2_rn(__fadd2_rn(f2s(c.x), f2(-acc_r.x, -acc_r.y)), dLr);
-          da = __ffma2_rn(__fadd2_rn(f2s(c.y), f2(-acc_g.x, -acc_g.y)), dLg, da);
-          da = __ffma2_rn(__fadd2_rn(f2s(c.z), f2(-acc_b.x, -acc_b.y)), dLb, da);
+          // acc = colour composited from everything BEHIND this entry (the reference's accum_rec);
+          // dL/dalpha = T * sum_ch (c - acc) dL_ch  -  T_final/(1-alpha) * bg.dL ; then acc += alpha (c - acc)
+          const float2 d_r = __fadd2_rn(f2s(c.x), f2(-acc_r.x, -acc_r.y));
+          const float2 d_g = __fadd2_rn(f2s(c.y), f2(-acc_g.x, -acc_g.y));
+          const float2 d_b = __fadd2_rn(f2s(c.z), f2(-acc_b.x, -acc_b.y));
+          float2 da = __ffma2_rn(d_b, dLb, __ffma2_rn(d_g, dLg, __fmul2_rn(d_r, dLr)));
           da = __fmul2_rn(da, T);
           da = __ffma2_rn(f2(-tf_bg.x, -tf_bg.y), inv, da);
           da.x = vA ? da.x : 0.f; da.y = vB ? da.y : 0.f;
+          acc_r = __ffma2_rn(am, d_r, acc_r);
+          acc_g = __ffma2_rn(am, d_g, acc_g);
+          acc_b = __ffma2_rn(am, d_b, acc_b);
           const float2 dG = __fmul2_rn(f2s(e1.y), da);           // dL/dG = opacity * dL/dalpha
           const float2 gdG = __fmul2_rn(G, dG);                  // G * dL/dG
           const float2 gy = __fmul2_rn(gdG, dy);                 // G dL/dG dy
@@ -1133,7 +1226,8 @@ static int make_inptrs(const GsbCamera* cam, const GsbGaussians* g, InPtrs& in) 
   GSB_REQUIRE(cam && g, "null camera / gaussians");
   GSB_REQUIRE(g->P >= 0, "P < 0");
   GSB_REQUIRE(cam->width > 0 && cam->height > 0, "image size");
-  GSB_REQUIRE(cam->width <= 65535 * kBlock && cam->height <= 65535 * kBlock, "image too large");
+  GSB_REQUIRE((long long)((cam->width + kBlock - 1) / kBlock) * ((cam->height + kBlock - 1) / kBlock) <= 65535,
+              "image too large (more than 65535 tiles)");
   GSB_REQUIRE(cam->sh_degree >= 0 && cam->sh_degree <= 3, "sh_degree must be 0..3");
   GSB_REQUIRE(cam->sh_coeffs >= 1 && cam->sh_coeffs <= 16, "sh_coeffs must be 1..16");
   GSB_REQUIRE((cam->sh_degree + 1) * (cam->sh_degree + 1) <= cam->sh_coeffs || g->colors_precomp,
@@ -1227,9 +1321,12 @@ extern "C" GSB_API int gsb_render(const GsbCamera* cam, int32_t P, void* geom, v
       k_ranges_gather<<<(unsigned)((R + kThreads - 1) / kThreads), kThreads, 0, st>>>((uint32_t)R, gv, bv); }
   }
   { ProfScope ps(GSB_K_BLEND_FWD, st);
-    if (g_blend_version == 2)
-      k_blend_fwd2<<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, out_color,
-                                                  iv.final_T, iv.n_contrib);
+    if (g_blend_version == 2 && g_stage_bulk)
+      k_blend_fwd2<true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, out_color,
+                                                        iv.final_T, iv.n_contrib);
+    else if (g_blend_version == 2)
+      k_blend_fwd2<false><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, out_color,
+                                                         iv.final_T, iv.n_contrib);
     else
       k_blend_fwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, out_color,
                                                 iv.final_T, iv.n_contrib); }
@@ -1259,9 +1356,12 @@ extern "C" GSB_API int gsb_backward(const GsbCamera* cam, const GsbGaussians* g,
   GSB_CUDA(cudaMemsetAsync(gv.dacc, 0, (size_t)P * 48, st));
   if (R > 0) {
     ProfScope ps(GSB_K_BLEND_BWD, st);
-    if (g_blend_version == 2)
-      k_blend_bwd2<<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, iv.final_T,
-                                                  iv.n_contrib, dL_dout, (float*)gv.dacc);
+    if (g_blend_version == 2 && g_stage_bulk)
+      k_blend_bwd2<true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, iv.final_T,
+                                                        iv.n_contrib, dL_dout, (float*)gv.dacc);
+    else if (g_blend_version == 2)
+      k_blend_bwd2<false><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, iv.final_T,
+                                                         iv.n_contrib, dL_dout, (float*)gv.dacc);
     else
       k_blend_bwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, iv.final_T,
                                                 iv.n_contrib, dL_dout, (float*)gv.dacc);

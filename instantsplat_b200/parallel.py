@@ -52,3 +52,59 @@ def init_from_env(backend: str = "nccl"):
         else:
             dist.init_process_group(backend, rank=rank, world_size=world)
     return rank, local, world
+
+
+# ----------------------------------------------------------------------------------------------
+# peer-visible device buffers (CUDA IPC) for the fused reduce-scatter -> Adam -> all-gather kernel
+# ----------------------------------------------------------------------------------------------
+class _DevMem:
+    """Exposes a raw device allocation through __cuda_array_interface__ so torch can view it."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False),
+                                         "version": 2}
+
+
+class PeerBuffer:
+    """A flat fp32 buffer allocated by libgsb200.so (cudaMalloc) on this rank's GPU and opened, through
+    CUDA IPC handles exchanged over torch.distributed, by every other rank of the node."""
+
+    def __init__(self, n_floats: int, device, group=None):
+        import ctypes
+        import torch.distributed as dist
+        from . import _lib
+        L = _lib.lib()
+        self.L, self.n = L, n_floats
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        with torch.cuda.device(device):
+            ptr = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            _lib.check(L.gsb_ipc_alloc(n_floats * 4, ctypes.byref(ptr), handle), "gsb_ipc_alloc")
+            self.local_ptr = ptr.value
+            handles = [None] * world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            self.ptrs = []
+            for r in range(world):
+                if r == rank:
+                    self.ptrs.append(self.local_ptr)
+                else:
+                    p = ctypes.c_void_p()
+                    _lib.check(L.gsb_ipc_open(handles[r], ctypes.byref(p)), f"gsb_ipc_open(rank {r})")
+                    self.ptrs.append(p.value)
+        self._mem = _DevMem(self.local_ptr, n_floats)
+        self.tensor = torch.as_tensor(self._mem, device=device)
+        self.rank, self.world = rank, world
+
+    def ptr_array(self):
+        import ctypes
+        return (ctypes.c_void_p * self.world)(*self.ptrs)
+
+
+def shard_bounds(total: int, world: int, rank: int, align: int = 768):
+    """Contiguous shard [lo, hi) of a flat buffer of `total` floats; boundaries are multiples of `align`
+    (a multiple of every row length with a per-row multiplier and of the 128-bit vector width)."""
+    per = (total + world - 1) // world
+    per = (per + align - 1) // align * align
+    lo = min(total, rank * per)
+    hi = min(total, lo + per)
+    return lo, hi

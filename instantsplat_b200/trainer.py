@@ -74,10 +74,13 @@ def _align(n, a=64):
 class JointTrainer:
     def __init__(self, scene: Scene, device, gt_images: Optional[torch.Tensor] = None,
                  cfg: Optional[OptimConfig] = None, world_size: int = 1, rank: int = 0,
-                 process_group=None):
+                 process_group=None, exchange: str = "allreduce"):
         self.cfg = cfg or OptimConfig()
         self.dev = torch.device(device)
         self.world_size, self.rank, self.pg = world_size, rank, process_group
+        if exchange not in ("allreduce", "fused_p2p"):
+            raise ValueError(f"unknown exchange mode {exchange!r}")
+        self.exchange = exchange if world_size > 1 else "allreduce"
         self.P = P = scene.P
         self.W, self.H = scene.width, scene.height
         self.sh_degree = scene.sh_degree
@@ -88,10 +91,22 @@ class JointTrainer:
             offs[name] = total
             total += _align(P * k)
         self.offs, self.total = offs, total
-        self.params = torch.zeros(total, dtype=torch.float32, device=self.dev)
-        self.grads = torch.zeros(total, dtype=torch.float32, device=self.dev)
-        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=self.dev)
-        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        if self.exchange == "fused_p2p":
+            # peer-visible parameter / gradient buffers (CUDA IPC) and shard-sized Adam moments
+            from .parallel import PeerBuffer, shard_bounds
+            self._peer_params = PeerBuffer(total, self.dev, process_group)
+            self._peer_grads = PeerBuffer(total, self.dev, process_group)
+            self.params, self.grads = self._peer_params.tensor, self._peer_grads.tensor
+            self.shard = shard_bounds(total, world_size, rank)
+            n_sh = max(4, self.shard[1] - self.shard[0])
+            self.exp_avg = torch.zeros(n_sh, dtype=torch.float32, device=self.dev)
+            self.exp_avg_sq = torch.zeros(n_sh, dtype=torch.float32, device=self.dev)
+            self._sync = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        else:
+            self.params = torch.zeros(total, dtype=torch.float32, device=self.dev)
+            self.grads = torch.zeros(total, dtype=torch.float32, device=self.dev)
+            self.exp_avg = torch.zeros(total, dtype=torch.float32, device=self.dev)
+            self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=self.dev)
         for name, k in SEGMENTS:
             self.view(self.params, name).copy_(scene.params[name].reshape(P, k).to(self.dev))
         self.poses = scene.poses.to(self.dev).float().contiguous()              # [n_views,7]
@@ -100,7 +115,9 @@ class JointTrainer:
         self.pose_v = torch.zeros_like(self.poses)
         self.per_point_lr = None
         if self.cfg.pp_optimizer and scene.per_point_lr is not None:
-            self.per_point_lr = scene.per_point_lr.to(self.dev).float().reshape(P).contiguous()
+            ppl = torch.ones(_align(P * 3) // 3 + 1, dtype=torch.float32, device=self.dev)   # covers the padded tail
+            ppl[:P] = scene.per_point_lr.to(self.dev).float().reshape(P)
+            self.per_point_lr = ppl
         self.gt = None if gt_images is None else gt_images.to(self.dev).float().contiguous()
         # ---- camera constants (identity view, reference gaussian_renderer/__init__.py:55-59)
         from .camera import projection_matrix
@@ -123,6 +140,7 @@ class JointTrainer:
         self.sums = torch.zeros(2, dtype=torch.float64, device=self.dev)
         self.host_r = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.flags = torch.zeros(8, dtype=torch.int32, device=self.dev)
+        self._pose_flags = torch.zeros(8, dtype=torch.int32, device=self.dev)
         self.iteration = 0
         self.opt_step = 0
         self.last_R = 0
@@ -222,7 +240,7 @@ class JointTrainer:
             from .parallel import allreduce_sum_
             allreduce_sum_((self.grads, self.pose_grad), self.pg)
 
-    def optimizer_step(self) -> None:
+    def optimizer_step(self, grad_scale: Optional[float] = None) -> None:
         """PerPointAdam.step over the 6 Gaussian tensors + the pose table in one launch
         (param groups and LRs of /root/reference/scene/gaussian_model.py:203-243)."""
         c = self.cfg
@@ -232,7 +250,7 @@ class JointTrainer:
         corr = (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
         lrs = dict(xyz=self.xyz_sched(self.iteration), f_dc=c.feature_lr * 10, f_rest=c.feature_lr / 20.0 * 10,
                    opacity=c.opacity_lr, scaling=c.scaling_lr * 10, rotation=c.rotation_lr * 10)
-        gs = 1.0 / self.world_size
+        gs = 1.0 / self.world_size if grad_scale is None else grad_scale
         entries = []
         for name, k in SEGMENTS:
             entries.append(dict(param=self.view(self.params, name), grad=self.view(self.grads, name),
@@ -246,6 +264,63 @@ class JointTrainer:
                                 beta1=b1, beta2=b2, eps=eps, weight_decay=0.0, grad_scale=gs))
         launch_adam(entries, self.flags)
 
+    def _lrs(self):
+        c = self.cfg
+        return dict(xyz=self.xyz_sched(self.iteration), f_dc=c.feature_lr * 10, f_rest=c.feature_lr / 20.0 * 10,
+                    opacity=c.opacity_lr, scaling=c.scaling_lr * 10, rotation=c.rotation_lr * 10)
+
+    def fused_exchange_step(self) -> None:
+        """Multi-GPU: gate flags + pose gradients all-reduced (tiny NCCL collectives that double as the
+        pre-barrier), then ONE kernel per rank doing reduce-scatter -> per-point Adam -> all-gather over
+        NVLink peer memory (csrc/gs_comm.cu), then a barrier before anyone reads the new parameters."""
+        import torch.distributed as dist
+        from ._lib import GsbAdamTensor, GsbShardPiece
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        c = self.cfg
+        self.opt_step += 1
+        t = self.opt_step
+        b1, b2, eps = 0.9, 0.999, 1e-15
+        corr = (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
+        lrs = self._lrs()
+        # 1. whole-tensor gates on the local gradients, OR-ed across ranks
+        arr = (GsbAdamTensor * len(SEGMENTS))()
+        for a, (name, k) in zip(arr, SEGMENTS):
+            g = self.view(self.grads, name)
+            a.param = a.exp_avg = a.exp_avg_sq = a.grad = g.data_ptr()
+            a.numel, a.row_len, a.grad_scale = g.numel(), k, 1.0
+            a.step_size, a.beta1, a.beta2, a.eps, a.weight_decay = 0.0, b1, b2, eps, 0.0
+        check(L.gsb_adam_gate(len(SEGMENTS), arr, self.flags.data_ptr(), st), "gsb_adam_gate")
+        dist.all_reduce(self.flags, op=dist.ReduceOp.MAX, group=self.pg)
+        dist.all_reduce(self.pose_grad, op=dist.ReduceOp.SUM, group=self.pg)
+        # 2. the fused kernel over this rank's shard
+        lo, hi = self.shard
+        pieces = []
+        for fi, (name, k) in enumerate(SEGMENTS):
+            s0 = self.offs[name]
+            s1 = s0 + _align(self.P * k)
+            b, e = max(lo, s0), min(hi, s1)
+            if e > b:
+                pc = GsbShardPiece()
+                pc.begin, pc.end, pc.seg_begin = b, e, s0
+                pc.per_point_lr = self.per_point_lr.data_ptr() if (name == "xyz" and self.per_point_lr is not None) else None
+                pc.row_len, pc.flag_index = k, fi
+                pc.step_size, pc.beta1, pc.beta2, pc.eps = lrs[name] * corr, b1, b2, eps
+                pieces.append(pc)
+        parr = (GsbShardPiece * max(1, len(pieces)))(*pieces)
+        check(L.gsb_fused_rs_adam_ag(self.world_size, self.rank, self._peer_grads.ptr_array(),
+                                     self._peer_params.ptr_array(), self.exp_avg.data_ptr(),
+                                     self.exp_avg_sq.data_ptr(), lo, len(pieces), parr, self.flags.data_ptr(),
+                                     1.0 / self.world_size, st), "gsb_fused_rs_adam_ag")
+        # 3. pose table: replicated Adam on the all-reduced pose gradients
+        if c.optim_pose:
+            launch_adam([dict(param=self.poses, grad=self.pose_grad, exp_avg=self.pose_m, exp_avg_sq=self.pose_v,
+                              per_point_lr=None, row_len=7, step_size=self.cam_sched(self.iteration) * corr,
+                              beta1=b1, beta2=b2, eps=eps, weight_decay=0.0, grad_scale=1.0 / self.world_size)],
+                        self._pose_flags)
+        # 4. nobody may start the next forward before every rank's parameter stores have landed
+        dist.all_reduce(self._sync, group=self.pg)
+
     def step(self, view: int, gt: Optional[torch.Tensor] = None) -> None:
         """One reference iteration on `view` (train.py:140-211)."""
         self.iteration += 1
@@ -253,8 +328,11 @@ class JointTrainer:
             gt = self.gt[view]
         self.render(view)
         self.loss_and_backward(view, gt)
-        self.reduce_grads()
-        self.optimizer_step()
+        if self.exchange == "fused_p2p":
+            self.fused_exchange_step()
+        else:
+            self.reduce_grads()
+            self.optimizer_step()
 
     # ------------------------------------------------------------------------------------------
     def algorithmic_bytes(self) -> Dict[str, float]:

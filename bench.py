@@ -209,8 +209,18 @@ def run_b200(args):
     torch.cuda.empty_cache()
     gt_host = gt_dev.cpu().pin_memory()
     tr = I.JointTrainer(sc, dev, gt_images=gt_dev, world_size=world, rank=rank, exchange=args.exchange)
-    stage = torch.empty_like(gt_dev[0])
-    loss_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+    # ---- e2e pipeline through the public API: this step's GT image is copied H2D from pinned memory on a copy
+    # stream (double buffered, so the copy of step s+1 overlaps the compute of step s) and every step's loss is
+    # read back to the host (asynchronously, consumed one step later).
+    stages = [torch.empty_like(gt_dev[0]) for _ in range(2)]
+    stage = stages[0]
+    loss_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_loss = [torch.cuda.Event() for _ in range(2)]
+    losses = []
+    e2e_state = {"primed": -1}
 
     def barrier():
         torch.cuda.synchronize()
@@ -221,13 +231,29 @@ def run_b200(args):
     def device_step(s):
         tr.step(view_for_step(sc.n_views, world, rank, s))
 
+    def prefetch(s):
+        i = s & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[i])
+            stages[i].copy_(gt_host[view_for_step(sc.n_views, world, rank, s)], non_blocking=True)
+            ev_copied[i].record(copy_stream)
+
     def e2e_step(s):
-        v = view_for_step(sc.n_views, world, rank, s)
-        stage.copy_(gt_host[v], non_blocking=True)            # H2D of this step's input from pinned memory
-        tr.step(v, gt=stage)
-        loss_host.copy_(tr.loss_value().reshape(1), non_blocking=True)   # D2H of the step's result
-        torch.cuda.current_stream().synchronize()
-        return float(loss_host[0])
+        i = s & 1
+        if e2e_state["primed"] != s:
+            prefetch(s)
+        prefetch(s + 1)
+        e2e_state["primed"] = s + 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev_copied[i])
+        tr.step(view_for_step(sc.n_views, world, rank, s), gt=stages[i])
+        ev_free[i].record(cur)
+        loss_host[i:i + 1].copy_(tr.loss_value().reshape(1), non_blocking=True)   # D2H of this step's result
+        ev_loss[i].record(cur)
+        if e2e_state.get("have_prev"):
+            ev_loss[1 - i].synchronize()
+            losses.append(float(loss_host[1 - i]))
+        e2e_state["have_prev"] = True
 
     def timed(fn, n, first):
         barrier()
@@ -317,7 +343,8 @@ def run_b200(args):
         "render_mpix_per_s_fwd_bwd": sc.width * sc.height / (t_render * 1e-3) / 1e6,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(stage.numel() * 4), "d2h_bytes_per_step": 8,
-                "api": "JointTrainer.step(view, gt=<pinned host image copied H2D>) + loss_value() D2H"},
+                "api": "JointTrainer.step(view, gt=<pinned host image, H2D on a copy stream, double buffered>) + "
+                       "loss_value() D2H every step"},
         "gpu_launches": launches, "gpu_launches_note": "libgsb200.so kernels only (cub sort/scan launches excluded)",
         "kernels": kernels, "roofline": roof, "clocks": clocks, "cpu_baseline": cpu_base, "impl": "b200",
     }

@@ -60,21 +60,49 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return r;   // valid in thread 0
 }
 
-// Stage a (TH+10) x (TW+10) halo of one plane into shared memory (zero 'same' padding).
+// Stage a (TH+10) x (TW+10) halo of one plane into shared memory (zero 'same' padding): one warp per
+// row, lanes along x (two coalesced accesses per row).  Fully unrolled with all global loads issued
+// before the first shared store, so a lane has 8 loads in flight per plane.
+constexpr int kRowsPerWarp = (EH + 7) / 8;   // 4
+struct HaloRegs { float a[kRowsPerWarp], b[kRowsPerWarp]; };
+
+__device__ __forceinline__ void halo_load(HaloRegs& h, const float* __restrict__ src, int H, int W, int x0, int y0) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int xa = x0 - HALO + lane, xb = xa + 32;
+  const bool xa_in = xa >= 0 && xa < W;
+  const bool xb_in = lane < TW + 2 * HALO - 32 && xb < W;
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) {
+    const int r = warp + 8 * i;
+    const int y = y0 + r - HALO;
+    const bool yin = r < EH && y >= 0 && y < H;
+    const float* row = src + (size_t)(yin ? y : 0) * W;
+    h.a[i] = (yin && xa_in) ? __ldg(row + xa) : 0.f;
+    h.b[i] = (yin && xb_in) ? __ldg(row + xb) : 0.f;
+  }
+}
+__device__ __forceinline__ void halo_store(const HaloRegs& h, float (*dst)[EWP]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) {
+    const int r = warp + 8 * i;
+    if (r < EH) {
+      dst[r][lane] = h.a[i];
+      if (lane < EWP - 32) dst[r][32 + lane] = h.b[i];
+    }
+  }
+}
 __device__ __forceinline__ void stage_plane(float (*dst)[EWP], const float* __restrict__ src, int H, int W,
                                             int x0, int y0) {
-  for (int k = threadIdx.x; k < EH * EWP; k += 256) {
-    int r = k / EWP, c = k - r * EWP;
-    int y = y0 + r - HALO, x = x0 + c - HALO;
-    bool in = (c < TW + 2 * HALO) && x >= 0 && x < W && y >= 0 && y < H;
-    dst[r][c] = in ? __ldg(src + (size_t)y * W + x) : 0.f;
-  }
+  HaloRegs h;
+  halo_load(h, src, H, W, x0, y0);
+  halo_store(h, dst);
 }
 
 // Register-tiled separable 11-tap filter.  Horizontal: thread -> (row, 4 adjacent columns), inputs
 // fetched with four 128-bit shared loads.  Vertical: thread -> (column, 2 adjacent rows).
 // img planes [BC][H][W].  maps (optional) [3][BC][H][W].  sums[0] += sum|a-b| (if do_l1), sums[1] += sum ssim.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_ssim_fwd(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
            double* __restrict__ sums, float* __restrict__ maps, size_t plane_total, int do_l1) {
   __shared__ __align__(16) float sA[EH][EWP];
@@ -83,8 +111,13 @@ k_ssim_fwd(int H, int W, const float* __restrict__ img1, const float* __restrict
   __shared__ float red[8];
   const int bc = blockIdx.z;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-  stage_plane(sA, img1 + (size_t)bc * H * W, H, W, x0, y0);
-  stage_plane(sB, img2 + (size_t)bc * H * W, H, W, x0, y0);
+  {
+    HaloRegs ha, hb;
+    halo_load(ha, img1 + (size_t)bc * H * W, H, W, x0, y0);
+    halo_load(hb, img2 + (size_t)bc * H * W, H, W, x0, y0);
+    halo_store(ha, sA);
+    halo_store(hb, sB);
+  }
   __syncthreads();
   if (threadIdx.x < EH * (TW / 4)) {
     const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
@@ -162,7 +195,7 @@ k_ssim_fwd(int H, int W, const float* __restrict__ img1, const float* __restrict
 }
 
 // out = ssim_scale * (conv(m_mu) + 2 x conv(m_s1) + y conv(m_s12)) [* *dyn_scale] + l1_scale * sign(x-y)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 k_ssim_bwd(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
            const float* __restrict__ maps, size_t plane_total, float ssim_scale,
            const float* __restrict__ dyn_scale, float l1_scale, float* __restrict__ out) {
@@ -171,9 +204,15 @@ k_ssim_bwd(int H, int W, const float* __restrict__ img1, const float* __restrict
   const int bc = blockIdx.z;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const size_t pbase = (size_t)bc * H * W;
-  stage_plane(sM[0], maps + pbase, H, W, x0, y0);
-  stage_plane(sM[1], maps + plane_total + pbase, H, W, x0, y0);
-  stage_plane(sM[2], maps + 2 * plane_total + pbase, H, W, x0, y0);
+  {
+    HaloRegs h0, h1, h2;
+    halo_load(h0, maps + pbase, H, W, x0, y0);
+    halo_load(h1, maps + plane_total + pbase, H, W, x0, y0);
+    halo_load(h2, maps + 2 * plane_total + pbase, H, W, x0, y0);
+    halo_store(h0, sM[0]);
+    halo_store(h1, sM[1]);
+    halo_store(h2, sM[2]);
+  }
   __syncthreads();
   if (threadIdx.x < EH * (TW / 4)) {
     const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;

@@ -113,6 +113,7 @@ void gsb_set_error(const char* s) { snprintf(g_err, sizeof(g_err), "%s", s); }
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 constexpr int kThreads = 256;
+constexpr int kPT = 128;         // threads (= Gaussians) per CTA in the per-Gaussian kernels
 constexpr int kRowPad = 49;      // shared-memory SH row stride (48 + 1, conflict-free)
 constexpr int kChunk = 256;      // slab entries staged per step in the blend kernels
 
@@ -165,7 +166,7 @@ static GeomView geom_view(void* base, int P) {
   v.offs = (uint32_t*)take(Pp * 4);
   v.clamped = (uint8_t*)take(Pp);
   v.dacc = (float4*)take(Pp * 48);
-  size_t nb = (Pp + kThreads - 1) / kThreads;
+  size_t nb = (Pp + kPT - 1) / kPT;
   v.pose_part = (float*)take(nb * 16 * 4);
   v.pose_acc = (float*)take(16 * 4);
   v.nrend = (uint32_t*)take(4);
@@ -340,43 +341,76 @@ __device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* 
   }
 }
 
-// Shared-memory layout of the two per-Gaussian kernels (dynamic):
-//   cam   : CamConst
-//   sh    : [256][49]  (dc in cols 0..2, rest in cols 3..47)
-//   geo   : [256][13]  (xyz 0..2, scale 3..5, quat 6..9, opacity 10; stride 13 is conflict-free)
-constexpr int kGeoPad = 13;
-constexpr size_t kPrepSmem = sizeof(CamConst) + 16 + (size_t)kThreads * (kRowPad + kGeoPad) * 4;
+// Shared-memory layout of the two per-Gaussian kernels (dynamic, floats, N = kPT Gaussians per CTA):
+//   cam | xyz[3N] | scale[3N] | quat[4N] | opacity[N] | sh[49N]
+// Every array is copied CONTIGUOUSLY (128-bit global loads -> 128-bit shared stores, conflict-free);
+// each thread then walks its own row with an odd word stride (3, 45; the quaternion is one LDS.128), so
+// the strided accesses are conflict-free too.  Split SH layout: dc at sh[3t], rest at sh[3N + 45t].
+// Packed [P,M,3] layout (generic B2 boundary): rows padded to kRowPad = 49 words.
+constexpr int kSmXyz = 0, kSmSc = 3 * kPT, kSmQ = 6 * kPT, kSmOp = 10 * kPT, kSmSh = 11 * kPT;
+constexpr int kSmFloats = 11 * kPT + kRowPad * kPT;
+constexpr size_t kPrepSmem = sizeof(CamConst) + 16 + (size_t)kSmFloats * 4;
 
-__device__ __forceinline__ void load_block_inputs(const InPtrs& in, int first, int nv, bool use_sh,
-                                                  int D, int M, float* sm_sh, float* sm_geo) {
-  bool vec = in.vec_ok != 0;
-  stage_in(sm_geo, in.means + (size_t)3 * first, 3 * nv, 3, kGeoPad, 0, vec);
-  if (in.scales) stage_in(sm_geo, in.scales + (size_t)3 * first, 3 * nv, 3, kGeoPad, 3, vec);
-  if (in.rots) stage_in(sm_geo, in.rots + (size_t)4 * first, 4 * nv, 4, kGeoPad, 6, vec);
-  stage_in(sm_geo, in.opac + first, nv, 1, kGeoPad, 10, vec);
+__device__ __forceinline__ void copy_in(float* sm, const float* __restrict__ src, int n, bool vec) {
+  if (vec) {
+    const int n4 = n >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(sm);
+    for (int k = threadIdx.x; k < n4; k += blockDim.x) d4[k] = __ldg(s4 + k);
+    for (int e = 4 * n4 + threadIdx.x; e < n; e += blockDim.x) sm[e] = __ldg(src + e);
+  } else {
+    for (int e = threadIdx.x; e < n; e += blockDim.x) sm[e] = __ldg(src + e);
+  }
+}
+__device__ __forceinline__ void copy_out(float* __restrict__ dst, const float* sm, int n, bool vec) {
+  if (vec) {
+    const int n4 = n >> 2;
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const float4* s4 = reinterpret_cast<const float4*>(sm);
+    for (int k = threadIdx.x; k < n4; k += blockDim.x) d4[k] = s4[k];
+    for (int e = 4 * n4 + threadIdx.x; e < n; e += blockDim.x) dst[e] = sm[e];
+  } else {
+    for (int e = threadIdx.x; e < n; e += blockDim.x) dst[e] = sm[e];
+  }
+}
+
+struct ShRows { int dc_stride, rest_off, rest_stride; };   // thread t: dc at sh[dc_stride*t], rest at sh[rest_off + rest_stride*t]
+__device__ __forceinline__ ShRows sh_rows(int sh_packed, int M) {
+  ShRows r;
+  if (sh_packed) { r.dc_stride = kRowPad; r.rest_off = 3; r.rest_stride = kRowPad; }
+  else { r.dc_stride = 3; r.rest_off = 3 * kPT; r.rest_stride = 3 * (M - 1); }
+  return r;
+}
+
+__device__ __forceinline__ void load_block_inputs(const InPtrs& in, int first, int nv, bool use_sh, int D, int M,
+                                                  float* sm) {
+  const bool vec = in.vec_ok != 0;
+  copy_in(sm + kSmXyz, in.means + (size_t)3 * first, 3 * nv, vec);
+  if (in.scales) copy_in(sm + kSmSc, in.scales + (size_t)3 * first, 3 * nv, vec);
+  if (in.rots) copy_in(sm + kSmQ, in.rots + (size_t)4 * first, 4 * nv, vec);
+  copy_in(sm + kSmOp, in.opac + first, nv, vec);
   if (use_sh) {
     if (in.sh_packed) {
-      stage_in(sm_sh, in.sh_dc + (size_t)3 * M * first, 3 * M * nv, 3 * M, kRowPad, 0, vec);
+      stage_in(sm + kSmSh, in.sh_dc + (size_t)3 * M * first, 3 * M * nv, 3 * M, kRowPad, 0, vec);
     } else {
-      stage_in(sm_sh, in.sh_dc + (size_t)3 * first, 3 * nv, 3, kRowPad, 0, vec);
+      copy_in(sm + kSmSh, in.sh_dc + (size_t)3 * first, 3 * nv, vec);
       if (D > 0 && M > 1)
-        stage_in(sm_sh, in.sh_rest + (size_t)3 * (M - 1) * first, 3 * (M - 1) * nv, 3 * (M - 1),
-                 kRowPad, 3, vec);
+        copy_in(sm + kSmSh + 3 * kPT, in.sh_rest + (size_t)3 * (M - 1) * first, 3 * (M - 1) * nv, vec);
     }
   }
 }
 
-__device__ __forceinline__ void read_gauss(const float* sm_geo, int t, bool has_sr, GaussIn& g) {
-  const float* r = sm_geo + t * kGeoPad;
-  g.m[0] = r[0]; g.m[1] = r[1]; g.m[2] = r[2];
+__device__ __forceinline__ void read_gauss(const float* sm, int t, bool has_sr, GaussIn& g) {
+  g.m[0] = sm[kSmXyz + 3 * t]; g.m[1] = sm[kSmXyz + 3 * t + 1]; g.m[2] = sm[kSmXyz + 3 * t + 2];
   if (has_sr) {
-    g.sc[0] = r[3]; g.sc[1] = r[4]; g.sc[2] = r[5];
-    g.q[0] = r[6]; g.q[1] = r[7]; g.q[2] = r[8]; g.q[3] = r[9];
+    g.sc[0] = sm[kSmSc + 3 * t]; g.sc[1] = sm[kSmSc + 3 * t + 1]; g.sc[2] = sm[kSmSc + 3 * t + 2];
+    const float4 q = *reinterpret_cast<const float4*>(sm + kSmQ + 4 * t);
+    g.q[0] = q.x; g.q[1] = q.y; g.q[2] = q.z; g.q[3] = q.w;
   } else {
     g.sc[0] = g.sc[1] = g.sc[2] = 1.f;
     g.q[0] = 1.f; g.q[1] = g.q[2] = g.q[3] = 0.f;
   }
-  g.op = r[10];
+  g.op = sm[kSmOp + t];
 }
 
 __device__ __forceinline__ uint32_t count_or_emit_tiles(const Proj& p, float qthr, int W, int H, int gx,
@@ -402,35 +436,35 @@ __device__ __forceinline__ uint32_t count_or_emit_tiles(const Proj& p, float qth
 // ------------------------------------------------------------------------------------------
 // k_preprocess
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kPT)
 k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CamConst* cam = reinterpret_cast<CamConst*>(smem_raw);
-  float* sm_sh = reinterpret_cast<float*>(smem_raw + ((sizeof(CamConst) + 15) / 16) * 16);
-  float* sm_geo = sm_sh + kThreads * kRowPad;
+  float* sm = reinterpret_cast<float*>(smem_raw + ((sizeof(CamConst) + 15) / 16) * 16);
   {
     const uint32_t* s = reinterpret_cast<const uint32_t*>(gv.cam);
     uint32_t* d = reinterpret_cast<uint32_t*>(cam);
     for (int k = threadIdx.x; k < (int)(sizeof(CamConst) / 4); k += blockDim.x) d[k] = s[k];
   }
-  int first = blockIdx.x * kThreads;
-  int nv = min(kThreads, in.P - first);
+  int first = blockIdx.x * kPT;
+  int nv = min(kPT, in.P - first);
   bool use_sh = in.colors == nullptr;
   __syncthreads();
-  load_block_inputs(in, first, nv, use_sh, cam->D, cam->M, sm_sh, sm_geo);
+  load_block_inputs(in, first, nv, use_sh, cam->D, cam->M, sm);
   __syncthreads();
   int t = threadIdx.x;
   if (t >= nv) return;
   int i = first + t;
   GaussIn g;
-  read_gauss(sm_geo, t, in.scales != nullptr, g);
+  read_gauss(sm, t, in.scales != nullptr, g);
   Proj p;
   project_geometry(*cam, g, in.cov3D ? in.cov3D + (size_t)6 * i : nullptr, p);
   float qthr = -1.f;
   uint32_t ntiles = 0;
   if (p.visible) {
     if (use_sh) {
-      project_color(*cam, sm_sh + t * kRowPad, sm_sh + t * kRowPad + 3, p);
+      { const ShRows sr = sh_rows(in.sh_packed, cam->M);
+        project_color(*cam, sm + kSmSh + sr.dc_stride * t, sm + kSmSh + sr.rest_off + sr.rest_stride * t, p); }
     } else {
       p.rgb[0] = in.colors[3 * i]; p.rgb[1] = in.colors[3 * i + 1]; p.rgb[2] = in.colors[3 * i + 2];
     }
@@ -1082,25 +1116,24 @@ struct OutPtrs {
   float* dsh_dc; float* dsh_rest; float* dcolors; float* dcov3D;
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kPT, 4)
 k_preprocess_bwd(InPtrs in, GeomView gv, const int* __restrict__ radii_unused, OutPtrs out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CamConst* cam = reinterpret_cast<CamConst*>(smem_raw);
-  float* sm_sh = reinterpret_cast<float*>(smem_raw + ((sizeof(CamConst) + 15) / 16) * 16);
-  float* sm_geo = sm_sh + kThreads * kRowPad;
-  __shared__ float s_pose[8][16];
+  float* sm = reinterpret_cast<float*>(smem_raw + ((sizeof(CamConst) + 15) / 16) * 16);
+  __shared__ float s_pose[kPT / 32][16];
   {
     const uint32_t* s = reinterpret_cast<const uint32_t*>(gv.cam);
     uint32_t* d = reinterpret_cast<uint32_t*>(cam);
     for (int k = threadIdx.x; k < (int)(sizeof(CamConst) / 4); k += blockDim.x) d[k] = s[k];
   }
-  const int first = blockIdx.x * kThreads;
-  const int nv = min(kThreads, in.P - first);
+  const int first = blockIdx.x * kPT;
+  const int nv = min(kPT, in.P - first);
   const bool use_sh = in.colors == nullptr;
   const bool vec = in.vec_ok != 0;
   __syncthreads();
   const int D = cam->D, M = cam->M;
-  load_block_inputs(in, first, nv, use_sh, D, M, sm_sh, sm_geo);
+  load_block_inputs(in, first, nv, use_sh, D, M, sm);
   __syncthreads();
   const int t = threadIdx.x;
   const int i = first + t;
@@ -1116,7 +1149,9 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int* __restrict__ radii_unused, O
   gg.dcolor[0] = gg.dcolor[1] = gg.dcolor[2] = 0.f;
   // Every thread touches only its own shared-memory rows from here on (no barrier needed until the
   // cooperative stores): the SH gradient is written IN PLACE over the staged SH row.
-  float* row = sm_sh + t * kRowPad;
+  const ShRows sr = sh_rows(in.sh_packed, M);
+  float* row_dc = sm + kSmSh + sr.dc_stride * t;
+  float* row_rest = sm + kSmSh + sr.rest_off + sr.rest_stride * t;
   bool has = false;
   if (t < nv) {
     float4 d0 = gv.dacc[3 * (size_t)i], d1 = gv.dacc[3 * (size_t)i + 1], d2 = gv.dacc[3 * (size_t)i + 2];
@@ -1126,22 +1161,22 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int* __restrict__ radii_unused, O
     for (int k = 0; k < 9; ++k) any |= (ds[k] != 0.f);
     if (any && gv.tiles[i] > 0) {
       GaussIn g;
-      read_gauss(sm_geo, t, in.scales != nullptr, g);
+      read_gauss(sm, t, in.scales != nullptr, g);
       Proj p;
       project_geometry(*cam, g, in.cov3D ? in.cov3D + (size_t)6 * i : nullptr, p);
       if (p.visible) {
         p.clamped = gv.clamped[i];
-        project_bwd(*cam, g, p, row + 3, use_sh, in.cov3D != nullptr, ds, gg, row, row + 3, pa);
+        project_bwd(*cam, g, p, row_rest, use_sh, in.cov3D != nullptr, ds, gg, row_dc, row_rest, pa);
         has = use_sh;
       }
     }
-    const int first_zero = has ? 3 * (D + 1) * (D + 1) : 0;     // inactive coefficients get zero gradient
-    for (int k = first_zero; k < 48; ++k) row[k] = 0.f;
-    float* r = sm_geo + t * kGeoPad;
-    r[0] = gg.dm[0]; r[1] = gg.dm[1]; r[2] = gg.dm[2];
-    r[3] = gg.dsc[0]; r[4] = gg.dsc[1]; r[5] = gg.dsc[2];
-    r[6] = gg.dq[0]; r[7] = gg.dq[1]; r[8] = gg.dq[2]; r[9] = gg.dq[3];
-    r[10] = gg.dop;
+    // inactive coefficients (and everything of a Gaussian that did not contribute) get zero gradient
+    if (!has) { row_dc[0] = 0.f; row_dc[1] = 0.f; row_dc[2] = 0.f; }
+    for (int k = has ? 3 * ((D + 1) * (D + 1) - 1) : 0; k < 3 * (M - 1); ++k) row_rest[k] = 0.f;
+    sm[kSmXyz + 3 * t] = gg.dm[0]; sm[kSmXyz + 3 * t + 1] = gg.dm[1]; sm[kSmXyz + 3 * t + 2] = gg.dm[2];
+    sm[kSmSc + 3 * t] = gg.dsc[0]; sm[kSmSc + 3 * t + 1] = gg.dsc[1]; sm[kSmSc + 3 * t + 2] = gg.dsc[2];
+    *reinterpret_cast<float4*>(sm + kSmQ + 4 * t) = make_float4(gg.dq[0], gg.dq[1], gg.dq[2], gg.dq[3]);
+    sm[kSmOp + t] = gg.dop;
     if (out.dmeans2D) {
       out.dmeans2D[3 * (size_t)i] = gg.dmeans2D[0];
       out.dmeans2D[3 * (size_t)i + 1] = gg.dmeans2D[1];
@@ -1157,18 +1192,17 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int* __restrict__ radii_unused, O
     }
   }
   __syncthreads();
-  if (out.dmeans) stage_out(out.dmeans + (size_t)3 * first, sm_geo, 3 * nv, 3, kGeoPad, 0, vec);
-  if (out.dscales) stage_out(out.dscales + (size_t)3 * first, sm_geo, 3 * nv, 3, kGeoPad, 3, vec);
-  if (out.drots) stage_out(out.drots + (size_t)4 * first, sm_geo, 4 * nv, 4, kGeoPad, 6, vec);
-  if (out.dopac) stage_out(out.dopac + first, sm_geo, nv, 1, kGeoPad, 10, vec);
+  if (out.dmeans) copy_out(out.dmeans + (size_t)3 * first, sm + kSmXyz, 3 * nv, vec);
+  if (out.dscales) copy_out(out.dscales + (size_t)3 * first, sm + kSmSc, 3 * nv, vec);
+  if (out.drots) copy_out(out.drots + (size_t)4 * first, sm + kSmQ, 4 * nv, vec);
+  if (out.dopac) copy_out(out.dopac + first, sm + kSmOp, nv, vec);
   if (use_sh && out.dsh_dc) {
     if (in.sh_packed) {
-      stage_out(out.dsh_dc + (size_t)3 * M * first, sm_sh, 3 * M * nv, 3 * M, kRowPad, 0, vec);
+      stage_out(out.dsh_dc + (size_t)3 * M * first, sm + kSmSh, 3 * M * nv, 3 * M, kRowPad, 0, vec);
     } else {
-      stage_out(out.dsh_dc + (size_t)3 * first, sm_sh, 3 * nv, 3, kRowPad, 0, vec);
+      copy_out(out.dsh_dc + (size_t)3 * first, sm + kSmSh, 3 * nv, vec);
       if (M > 1 && out.dsh_rest)
-        stage_out(out.dsh_rest + (size_t)3 * (M - 1) * first, sm_sh, 3 * (M - 1) * nv, 3 * (M - 1),
-                  kRowPad, 3, vec);
+        copy_out(out.dsh_rest + (size_t)3 * (M - 1) * first, sm + kSmSh + 3 * kPT, 3 * (M - 1) * nv, vec);
     }
   }
   // pose-gradient partials: warp shuffle, then across the 8 warps
@@ -1185,7 +1219,7 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int* __restrict__ radii_unused, O
     if (threadIdx.x < 16) {
       float v = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) v += s_pose[w][threadIdx.x];
+      for (int w = 0; w < kPT / 32; ++w) v += s_pose[w][threadIdx.x];
       gv.pose_part[(size_t)blockIdx.x * 16 + threadIdx.x] = v;
     }
   }
@@ -1280,8 +1314,8 @@ extern "C" GSB_API int gsb_preprocess(const GsbCamera* cam, const GsbGaussians* 
   if (P == 0) {
     GSB_CUDA(cudaMemsetAsync(gv.nrend, 0, 4, st));
   } else {
-    const int nb = (P + kThreads - 1) / kThreads;
-    { ProfScope ps(GSB_K_PREPROCESS, st); k_preprocess<<<nb, kThreads, kPrepSmem, st>>>(in, gv, radii); }
+    const int nb = (P + kPT - 1) / kPT;
+    { ProfScope ps(GSB_K_PREPROCESS, st); k_preprocess<<<nb, kPT, kPrepSmem, st>>>(in, gv, radii); }
     size_t tb = gv.cub_bytes;
     { ProfScope ps(GSB_K_SORT_DEPTH, st, 0);
       GSB_CUDA(cub::DeviceRadixSort::SortPairs(gv.cub_tmp, tb, gv.dkey, gv.dkey_s, gv.iota, gv.order, P, 0, 32, st)); }
@@ -1373,9 +1407,9 @@ extern "C" GSB_API int gsb_backward(const GsbCamera* cam, const GsbGaussians* g,
   uintptr_t a = (uintptr_t)out.dmeans | (uintptr_t)out.dscales | (uintptr_t)out.drots | (uintptr_t)out.dopac |
                 (uintptr_t)out.dsh_dc | (uintptr_t)out.dsh_rest;
   if (a & 15) in.vec_ok = 0;
-  const int nb = (P + kThreads - 1) / kThreads;
+  const int nb = (P + kPT - 1) / kPT;
   { ProfScope ps(GSB_K_PREPROCESS_BWD, st, g->pose ? 2 : 1);
-    k_preprocess_bwd<<<nb, kThreads, kPrepSmem, st>>>(in, gv, nullptr, out);
+    k_preprocess_bwd<<<nb, kPT, kPrepSmem, st>>>(in, gv, nullptr, out);
     if (g->pose) k_pose_finalize<<<1, 256, 0, st>>>(gv.pose_part, nb, g->pose, grads->dL_dpose); }
   GSB_CUDA(cudaGetLastError());
   return GSB_OK;

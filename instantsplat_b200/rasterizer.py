@@ -110,7 +110,9 @@ def _forward(settings, means3D, scales, rotations, opacities, sh_dc, sh_rest, sh
 
 
 def _backward(st: _State, dL_dout, want, dev):
-    """want: dict name -> bool.  Returns dict of grad tensors (dense)."""
+    """want: None (everything) or a set of names to compute; gradients that are not wanted are neither
+    allocated nor written by the kernels (e.g. the pose-only test-view optimisation of
+    /root/reference/render.py:99-170 passes {"pose"}).  Returns dict of dense grad tensors."""
     L = _lib.lib()
     P, M = st.P, st.M
     dL = f32c(dL_dout)
@@ -118,6 +120,8 @@ def _backward(st: _State, dL_dout, want, dev):
     out = {}
 
     def alloc(name, shape, field):
+        if want is not None and name not in want:
+            return
         t = torch.empty(shape, dtype=torch.float32, device=dev)
         out[name] = t
         setattr(gr, field, t.data_ptr())
@@ -140,7 +144,9 @@ def _backward(st: _State, dL_dout, want, dev):
             if M > 1:
                 alloc("sh_rest", (P, M - 1, 3), "dL_dsh_rest")
     if st.has_pose:
-        alloc("pose", (7,), "dL_dpose")
+        t = torch.empty(7, dtype=torch.float32, device=dev)     # always required by the ABI when pose is fused
+        out["pose"] = t
+        gr.dL_dpose = t.data_ptr()
     check(L.gsb_backward(ctypes.byref(st.cam), ctypes.byref(st.g), st.geom.data_ptr(), st.binning.data_ptr(),
                          st.R, st.image.data_ptr(), dL.data_ptr(), ctypes.byref(gr), _lib.stream_ptr()),
           "gsb_backward")
@@ -198,13 +204,19 @@ class _RasterizeFused(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out_color, _grad_radii):
         st = ctx.st
-        g = _backward(st, grad_out_color, None, grad_out_color.device)
+        need = ctx.needs_input_grad      # xyz, rotation, scaling, opacity, f_dc, f_rest, pose, means2D, settings
+        names = ("means3D", "rotations", "scales", "opacities", "sh_dc", "sh_rest", "pose", "means2D")
+        want = {n for n, k in zip(names, need) if k}
+        g = _backward(st, grad_out_color, want, grad_out_color.device)
         osh, dsh, rsh = ctx.shapes
         g_rest = g.get("sh_rest")
-        if g_rest is None and rsh is not None:
+        if g_rest is None and rsh is not None and need[5]:
             g_rest = torch.zeros(rsh, dtype=torch.float32, device=grad_out_color.device)
-        return (g["means3D"], g["rotations"], g["scales"], g["opacities"].reshape(osh),
-                g["sh_dc"].reshape(dsh), g_rest, g["pose"], g["means2D"], None)
+        g_op = g.get("opacities")
+        g_dc = g.get("sh_dc")
+        return (g.get("means3D"), g.get("rotations"), g.get("scales"),
+                None if g_op is None else g_op.reshape(osh), None if g_dc is None else g_dc.reshape(dsh), g_rest,
+                g.get("pose") if need[6] else None, g.get("means2D"), None)
 
 
 def rasterize_fused(xyz, rotation, scaling, opacity, f_dc, f_rest, pose, means2D, raster_settings):

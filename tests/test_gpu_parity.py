@@ -441,6 +441,23 @@ def test_render_dropin_matches_oracle_and_populates_grads():
     assert pkg["visibility_filter"].dtype == torch.bool
 
 
+def test_pose_only_tracking_mode():
+    """render.py:99-170 -- Gaussians frozen, only the camera pose requires grad: same pose gradient as the
+    full backward, no per-Gaussian gradient tensors produced."""
+    import instantsplat_b200 as I
+    sc = random_scene(4000, 128, 96, seed=44)
+    gt = torch.rand(3, sc.height, sc.width, generator=torch.Generator().manual_seed(1))
+    _, _, _, g_full = cuda_run(sc, 3, torch.zeros(3), gt)
+    prm = {k: v.to(DEV).clone() for k, v in sc.params.items()}                 # frozen
+    pose = sc.poses[0].to(DEV).clone().requires_grad_(True)
+    rs = settings_for(sc, 3, torch.zeros(3))
+    img, _ = I.rasterize_fused(prm["xyz"], prm["rotation"], prm["scaling"], prm["opacity"], prm["f_dc"],
+                               prm["f_rest"], pose, torch.zeros(sc.P, 3, device=DEV), rs)
+    I.fused_training_loss(img, gt.to(DEV)).backward()
+    assert rel_err(pose.grad, g_full["pose"]) < 1e-5
+    assert all(v.grad is None for v in prm.values())
+
+
 def test_trainer_step_matches_autograd_path_and_learns():
     import instantsplat_b200 as I
     sc = surface_scene(30_000, 3, 192, 128, seed=41, sh_degree=3)

@@ -115,7 +115,17 @@ static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a
 constexpr int kThreads = 256;
 constexpr int kPT = 128;         // threads (= Gaussians) per CTA in the per-Gaussian kernels
 constexpr int kRowPad = 49;      // shared-memory SH row stride (48 + 1, conflict-free)
-constexpr int kChunk = 256;      // slab entries staged per step in the blend kernels
+#ifndef GSB_CHUNK
+#define GSB_CHUNK 256
+#endif
+#ifndef GSB_FWD_MINB
+#define GSB_FWD_MINB 7
+#endif
+#ifndef GSB_BWD_MINB
+#define GSB_BWD_MINB 6
+#endif
+constexpr int kChunk1 = 256;           // v1 blend kernels: one entry per thread
+constexpr int kChunk = GSB_CHUNK;      // slab entries staged per step in the blend kernels
 
 struct GeomView {
   CamConst* cam;
@@ -382,9 +392,56 @@ __device__ __forceinline__ ShRows sh_rows(int sh_packed, int M) {
   return r;
 }
 
+// Full-CTA fast path (aligned pointers, split SH layout with 16 coefficients): all 128-bit global loads of
+// every array are issued before the first shared store, so each thread has ~15 independent 16-byte loads in
+// flight (memory-level parallelism instead of a load->store loop).
+template <int NF4, int MAXIT>
+__device__ __forceinline__ void ld_batch(float4 (&r)[MAXIT], const float* __restrict__ src) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int i = 0; i < MAXIT; ++i) {
+    const int k = threadIdx.x + i * kPT;
+    if (k < NF4) r[i] = __ldg(s4 + k);
+  }
+}
+template <int NF4, int MAXIT>
+__device__ __forceinline__ void st_batch(const float4 (&r)[MAXIT], float* sm) {
+  float4* d4 = reinterpret_cast<float4*>(sm);
+#pragma unroll
+  for (int i = 0; i < MAXIT; ++i) {
+    const int k = threadIdx.x + i * kPT;
+    if (k < NF4) d4[k] = r[i];
+  }
+}
+
+__device__ __forceinline__ void load_block_inputs_full(const InPtrs& in, int first, bool use_sh, int D, float* sm) {
+  constexpr int N3 = 3 * kPT / 4, N4 = kPT, N1 = kPT / 4, NR = 45 * kPT / 4;
+  float4 rx[1], rs[1], rq[1], ro[1], rd[1], rr[(NR + kPT - 1) / kPT];
+  ld_batch<N3, 1>(rx, in.means + (size_t)3 * first);
+  ld_batch<N3, 1>(rs, in.scales + (size_t)3 * first);
+  ld_batch<N4, 1>(rq, in.rots + (size_t)4 * first);
+  ld_batch<N1, 1>(ro, in.opac + first);
+  if (use_sh) {
+    ld_batch<N3, 1>(rd, in.sh_dc + (size_t)3 * first);
+    if (D > 0) ld_batch<NR, (NR + kPT - 1) / kPT>(rr, in.sh_rest + (size_t)45 * first);
+  }
+  st_batch<N3, 1>(rx, sm + kSmXyz);
+  st_batch<N3, 1>(rs, sm + kSmSc);
+  st_batch<N4, 1>(rq, sm + kSmQ);
+  st_batch<N1, 1>(ro, sm + kSmOp);
+  if (use_sh) {
+    st_batch<N3, 1>(rd, sm + kSmSh);
+    if (D > 0) st_batch<NR, (NR + kPT - 1) / kPT>(rr, sm + kSmSh + 3 * kPT);
+  }
+}
+
 __device__ __forceinline__ void load_block_inputs(const InPtrs& in, int first, int nv, bool use_sh, int D, int M,
                                                   float* sm) {
   const bool vec = in.vec_ok != 0;
+  if (vec && nv == kPT && in.scales && in.rots && (!use_sh || (!in.sh_packed && M == 16))) {
+    load_block_inputs_full(in, first, use_sh, D, sm);
+    return;
+  }
   copy_in(sm + kSmXyz, in.means + (size_t)3 * first, 3 * nv, vec);
   if (in.scales) copy_in(sm + kSmSc, in.scales + (size_t)3 * first, 3 * nv, vec);
   if (in.rots) copy_in(sm + kSmQ, in.rots + (size_t)4 * first, 4 * nv, vec);
@@ -568,7 +625,7 @@ __global__ void __launch_bounds__(kThreads)
 k_blend_fwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
             const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
             float* __restrict__ out_color, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
-  __shared__ float4 sm0[kChunk], sm1[kChunk], sm2[kChunk];
+  __shared__ float4 sm0[kChunk1], sm1[kChunk1], sm2[kChunk1];
   const int tile = blockIdx.x;
   const int tx = tile % gx, ty = tile / gx;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -584,8 +641,8 @@ k_blend_fwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, con
   uint32_t last = 0;
   bool done = !inside;
   bool wdone = !(sx0 < W && sy0 < H);
-  for (int base = 0; base < n; base += kChunk) {
-    const int cnt = min(kChunk, n - base);
+  for (int base = 0; base < n; base += kChunk1) {
+    const int cnt = min(kChunk1, n - base);
     if ((int)threadIdx.x < cnt) {
       size_t e = (size_t)rg.x + base + threadIdx.x;
       sm0[threadIdx.x] = s0[e];
@@ -683,7 +740,7 @@ k_blend_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, con
             const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
             const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
             const float* __restrict__ dL_dpix, float* __restrict__ dacc) {
-  __shared__ float4 sm0[kChunk], sm1[kChunk], sm2[kChunk];
+  __shared__ float4 sm0[kChunk1], sm1[kChunk1], sm2[kChunk1];
   __shared__ int s_bmax;
   const int tile = blockIdx.x;
   const int tx = tile % gx, ty = tile / gx;
@@ -711,10 +768,10 @@ k_blend_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, con
   const int bmax = s_bmax;
   float T = T_final;
   float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, last_alpha = 0.f, last_r = 0.f, last_g = 0.f, last_b = 0.f;
-  const int nchunks = (bmax + kChunk - 1) / kChunk;
+  const int nchunks = (bmax + kChunk1 - 1) / kChunk1;
   for (int ch = nchunks - 1; ch >= 0; --ch) {
-    const int base = ch * kChunk;
-    const int cnt = min(kChunk, bmax - base);
+    const int base = ch * kChunk1;
+    const int cnt = min(kChunk1, bmax - base);
     if ((int)threadIdx.x < cnt) {
       size_t e = (size_t)rg.x + base + threadIdx.x;
       sm0[threadIdx.x] = s0[e];
@@ -858,7 +915,7 @@ __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b
 __device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
 
 template <bool BULK>
-__global__ void __launch_bounds__(kThreads2, 7)
+__global__ void __launch_bounds__(kThreads2, GSB_FWD_MINB)
 k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
              const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
              float* __restrict__ out_color, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
@@ -967,7 +1024,7 @@ k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
 }
 
 template <bool BULK>
-__global__ void __launch_bounds__(kThreads2, 6)
+__global__ void __launch_bounds__(kThreads2, GSB_BWD_MINB)
 k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
              const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
              const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,

@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json configs index (2 = headline)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink P (debug only; invalidates the number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--blend-version", type=int, default=0, help="debug: force blend kernel version 1|2|3")
     ap.add_argument("--exchange", default="fused_p2p", choices=["allreduce", "fused_p2p"],
                     help="multi-GPU gradient exchange: NCCL all-reduce + Adam, or the fused P2P "
                          "reduce-scatter->Adam->all-gather kernel (default)")
@@ -198,6 +199,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     L = I.lib()
+    if args.blend_version:
+        L.gsb_set_option(b"blend_version", args.blend_version)
     sc = make_config(args.config, args.scale)
     # ground-truth images: our own render of a perturbed copy of the scene (non-trivial loss)
     tgt = I.JointTrainer(sc, dev)

@@ -195,7 +195,8 @@ enum {
 GSB_API void gsb_profile_enable(int on);
 GSB_API int gsb_profile_collect(double* ms_sum, int64_t* count, int n_ids);
 GSB_API uint64_t gsb_launch_count(void);
-/* Tuning switches: "blend_version" = 1 (one pixel per lane) | 2 (two pixels per lane, packed f32x2; default);
+/* Tuning switches: "blend_version" = 1 (one pixel per lane) | 2 (two pixels per lane, packed f32x2; default) | 3 (four
+ * pixels per lane, 2 warps per tile; slower, experiment);
  * "stage_bulk" = 1 (slab chunks staged with cp.async.bulk/TMA + mbarrier, double buffered; default) | 0. */
 GSB_API int gsb_set_option(const char* name, int value);
 

@@ -42,28 +42,37 @@ __device__ __forceinline__ int find_tensor(const AdamArgs& a, unsigned int b) {
 }
 
 // flags[k] = 1 when tensor k's (scaled, decayed) gradient has any element with g*g > 0.
-// Small persistent grid: each CTA strides over the block-sized chunks and stops as soon as the flag of
-// the tensor it is looking at is set, so the usual cost is a single wave of loads (a few microseconds).
-__global__ void __launch_bounds__(kAT) k_adam_gate(AdamArgs a, unsigned int* flags, unsigned int total_blocks) {
+// Grid = n_tensors x kGateSlots CTAs: CTA (k, j) scans chunks j, j+kGateSlots, ... of tensor k and re-reads
+// the flag before every chunk after its first, so in the usual case (some gradient is non-zero) each CTA
+// touches one chunk and the whole gate costs a few microseconds; an all-zero tensor is scanned completely.
+constexpr int kGateSlots = 84;
+__global__ void __launch_bounds__(kAT) k_adam_gate(AdamArgs a, unsigned int* flags) {
+  const int k = blockIdx.x / kGateSlots;
+  const unsigned int slot = blockIdx.x - k * kGateSlots;
+  const AdamT& t = a.t[k];
   __shared__ unsigned int s_set;
-  for (unsigned int vb = blockIdx.x; vb < total_blocks; vb += gridDim.x) {
-    const int k = find_tensor(a, vb);
-    const AdamT& t = a.t[k];
-    __syncthreads();
-    if (threadIdx.x == 0) s_set = *((volatile unsigned int*)(flags + k));
-    __syncthreads();
-    if (s_set) continue;
-    long long base = (long long)(vb - t.first_block) * kPerBlock;
+  for (unsigned int vb = slot; vb < t.nblocks; vb += kGateSlots) {
+    if (vb != slot) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_set = *((volatile unsigned int*)(flags + k));
+      __syncthreads();
+      if (s_set) return;
+    }
+    const long long base = (long long)vb * kPerBlock;
     bool any = false;
+#pragma unroll
     for (int u = 0; u < kPerThread; ++u) {
-      long long e = base + (long long)u * kAT + threadIdx.x;
+      const long long e = base + (long long)u * kAT + threadIdx.x;
       if (e < t.numel) {
         float g = t.g[e] * t.gscale;
         if (t.wd != 0.f) g += t.wd * t.p[e];
         any |= (g * g > 0.f);
       }
     }
-    if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(flags + k, 1u);
+    if (__syncthreads_or(any)) {
+      if (threadIdx.x == 0) atomicOr(flags + k, 1u);
+      return;
+    }
   }
 }
 
@@ -168,7 +177,7 @@ extern "C" GSB_API int gsb_adam_gate(int32_t n, const GsbAdamTensor* ts, uint32_
   cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, st);
   if (e == cudaSuccess && nb > 0) {
     gsb_count_launch(1);
-    k_adam_gate<<<(nb < 592u ? nb : 592u), kAT, 0, st>>>(a, flags, nb);
+    k_adam_gate<<<n * kGateSlots, kAT, 0, st>>>(a, flags);
     e = cudaGetLastError();
   }
   return finish(e, "gsb_adam_gate");
@@ -189,7 +198,7 @@ extern "C" GSB_API int gsb_adam_step(int32_t n, const GsbAdamTensor* ts, uint32_
   if (e == cudaSuccess && nb > 0) {
     gsb_count_launch(2);
     int slot = gsb_prof_begin(GSB_K_ADAM, st);
-    k_adam_gate<<<(nb < 592u ? nb : 592u), kAT, 0, st>>>(a, flags, nb);
+    k_adam_gate<<<n * kGateSlots, kAT, 0, st>>>(a, flags);
     k_adam<<<nb, kAT, 0, st>>>(a, flags);
     gsb_prof_end(slot, st);
     e = cudaGetLastError();

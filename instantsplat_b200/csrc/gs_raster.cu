@@ -92,9 +92,10 @@ extern "C" GSB_API int gsb_profile_collect(double* ms_sum, int64_t* count, int n
 extern "C" GSB_API uint64_t gsb_launch_count(void) { return g_launches; }
 static int g_blend_version = 2;
 static int g_stage_bulk = 1;   // 1: slabs staged with cp.async.bulk (TMA) + mbarrier, 0: cooperative loads
-// option "blend_version": 1 = one pixel per lane (8 warps / tile), 2 = two pixels per lane + packed f32x2
+// option "blend_version": 1 = one pixel per lane (8 warps / tile), 2 = two pixels per lane + packed f32x2 (default),
+// 3 = four pixels per lane (2 warps / tile; measured ~10 % slower than v2 on B200, kept as an experiment)
 extern "C" GSB_API int gsb_set_option(const char* name, int value) {
-  if (name && strcmp(name, "blend_version") == 0 && (value == 1 || value == 2)) { g_blend_version = value; return GSB_OK; }
+  if (name && strcmp(name, "blend_version") == 0 && value >= 1 && value <= 3) { g_blend_version = value; return GSB_OK; }
   if (name && strcmp(name, "stage_bulk") == 0 && (value == 0 || value == 1)) { g_stage_bulk = value; return GSB_OK; }
   snprintf(g_err, sizeof(g_err), "gsb_set_option: unknown option or bad value");
   return GSB_ERR_INVALID;
@@ -490,6 +491,55 @@ __device__ __forceinline__ uint32_t count_or_emit_tiles(const Proj& p, float qth
   return n;
 }
 
+// Gaussians whose rect spans more than kCoopTiles tiles are handled by the WHOLE WARP (one tile per lane per
+// step, ballot-ranked so the emission order stays row-major) instead of one thread looping over thousands of
+// tiles -- the per-thread loop is a performance cliff once a few Gaussians grow large.  Must be called by all
+// 32 lanes; `mine` says whether this lane's Gaussian wants the cooperative path.  Returns the lane's count.
+constexpr int kCoopTiles = 24;
+__device__ __forceinline__ uint32_t coop_count_or_emit(bool mine, const Proj& p, float qthr, int W, int H, int gx,
+                                                       tkey_t* keys, uint32_t* vals, uint32_t id) {
+  const int lane = threadIdx.x & 31;
+  uint32_t result = 0;
+  unsigned big = __ballot_sync(0xffffffffu, mine);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const float bx = __shfl_sync(0xffffffffu, p.x, src), by = __shfl_sync(0xffffffffu, p.y, src);
+    const float bA = __shfl_sync(0xffffffffu, p.A, src), bB = __shfl_sync(0xffffffffu, p.B, src);
+    const float bC = __shfl_sync(0xffffffffu, p.C, src), bq = __shfl_sync(0xffffffffu, qthr, src);
+    const int x0t = __shfl_sync(0xffffffffu, p.rx0, src), x1t = __shfl_sync(0xffffffffu, p.rx1, src);
+    const int y0t = __shfl_sync(0xffffffffu, p.ry0, src), y1t = __shfl_sync(0xffffffffu, p.ry1, src);
+    const uint32_t bid = __shfl_sync(0xffffffffu, id, src);
+    unsigned long long kp = (unsigned long long)keys, vp = (unsigned long long)vals;
+    kp = __shfl_sync(0xffffffffu, kp, src);
+    vp = __shfl_sync(0xffffffffu, vp, src);
+    tkey_t* bkeys = (tkey_t*)kp;
+    uint32_t* bvals = (uint32_t*)vp;
+    const int w = x1t - x0t, n = w * (y1t - y0t);
+    uint32_t run = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      bool keep = false;
+      int tx = 0, ty = 0;
+      if (i < n) {
+        ty = y0t + i / w; tx = x0t + i - (i / w) * w;
+        const float x0 = (float)(tx * kBlock), y0 = (float)(ty * kBlock);
+        const float x1 = fminf(x0 + kBlock - 1, (float)(W - 1)), y1 = fminf(y0 + kBlock - 1, (float)(H - 1));
+        keep = rect_may_contribute(bx, by, bA, bB, bC, bq, x0, y0, x1, y1);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep && bkeys) {
+        const uint32_t pos = run + __popc(m & ((1u << lane) - 1u));
+        bkeys[pos] = (tkey_t)(ty * gx + tx);
+        bvals[pos] = bid;
+      }
+      run += __popc(m);
+    }
+    if (lane == src) result = run;
+  }
+  return result;
+}
+
 // ------------------------------------------------------------------------------------------
 // k_preprocess
 // ------------------------------------------------------------------------------------------
@@ -509,27 +559,38 @@ k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
   __syncthreads();
   load_block_inputs(in, first, nv, use_sh, cam->D, cam->M, sm);
   __syncthreads();
-  int t = threadIdx.x;
-  if (t >= nv) return;
-  int i = first + t;
+  const int t = threadIdx.x;
+  const bool active = t < nv;
+  const int i = first + (active ? t : 0);
   GaussIn g;
-  read_gauss(sm, t, in.scales != nullptr, g);
+  read_gauss(sm, active ? t : 0, in.scales != nullptr, g);
   Proj p;
   project_geometry(*cam, g, in.cov3D ? in.cov3D + (size_t)6 * i : nullptr, p);
+  if (!active) p.visible = 0;
   float qthr = -1.f;
   uint32_t ntiles = 0;
+  bool coop = false;
   if (p.visible) {
     if (use_sh) {
-      { const ShRows sr = sh_rows(in.sh_packed, cam->M);
-        project_color(*cam, sm + kSmSh + sr.dc_stride * t, sm + kSmSh + sr.rest_off + sr.rest_stride * t, p); }
+      const ShRows sr = sh_rows(in.sh_packed, cam->M);
+      project_color(*cam, sm + kSmSh + sr.dc_stride * t, sm + kSmSh + sr.rest_off + sr.rest_stride * t, p);
     } else {
       p.rgb[0] = in.colors[3 * i]; p.rgb[1] = in.colors[3 * i + 1]; p.rgb[2] = in.colors[3 * i + 2];
     }
     qthr = cull_threshold(p.opacity);
-    ntiles = count_or_emit_tiles(p, qthr, cam->W, cam->H, cam->gx, in.exact_cull != 0, nullptr, nullptr, 0);
+    const int area = (p.rx1 - p.rx0) * (p.ry1 - p.ry0);
+    if (in.exact_cull == 0) ntiles = (uint32_t)area;
+    else if (qthr < 0.f) ntiles = 0;
+    else if (area > kCoopTiles) coop = true;
+    else ntiles = count_or_emit_tiles(p, qthr, cam->W, cam->H, cam->gx, true, nullptr, nullptr, 0);
   } else {
     p.x = p.y = p.A = p.B = p.C = 0.f; p.rgb[0] = p.rgb[1] = p.rgb[2] = 0.f;
   }
+  {
+    const uint32_t c = coop_count_or_emit(coop, p, qthr, cam->W, cam->H, cam->gx, nullptr, nullptr, 0);
+    if (coop) ntiles = c;
+  }
+  if (!active) return;
   gv.xyAB[i] = make_float4(p.x, p.y, p.A, p.B);
   gv.Codq[i] = make_float4(p.C, p.opacity, p.depth, qthr);
   gv.rgbr[i] = make_float4(p.rgb[0], p.rgb[1], p.rgb[2], (float)p.radius);
@@ -556,19 +617,32 @@ __global__ void k_store_total(const uint32_t* offs, int P, uint32_t* nrend) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 k_duplicate(int P, GeomView gv, BinView bv, int W, int H, int gx, int exact_cull, uint32_t R) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= P) return;
-  uint32_t i = gv.order[j];
-  uint32_t n = gv.tiles[i];
-  if (n == 0) return;
-  uint32_t off = gv.offs[j] - n;
-  if (off + n > R) return;   // defensive: never write past the binning buffer
-  float4 a = gv.xyAB[i], b = gv.Codq[i];
-  uint2 rc = gv.rect[i];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t i = 0, n = 0, off = 0;
+  if (j < P) {
+    i = gv.order[j];
+    n = gv.tiles[i];
+    if (n) {
+      off = gv.offs[j] - n;
+      if (off + n > R) n = 0;   // defensive: never write past the binning buffer
+    }
+  }
   Proj p;
-  p.x = a.x; p.y = a.y; p.A = a.z; p.B = a.w; p.C = b.x;
-  p.rx0 = rc.x & 0xFFFF; p.rx1 = rc.x >> 16; p.ry0 = rc.y & 0xFFFF; p.ry1 = rc.y >> 16;
-  count_or_emit_tiles(p, b.w, W, H, gx, exact_cull != 0, bv.keys + off, bv.vals + off, i);
+  p.x = p.y = p.A = p.B = p.C = 0.f;
+  p.rx0 = p.rx1 = p.ry0 = p.ry1 = 0;
+  float qthr = -1.f;
+  bool coop = false;
+  if (n) {
+    const float4 a = gv.xyAB[i], b = gv.Codq[i];
+    const uint2 rc = gv.rect[i];
+    p.x = a.x; p.y = a.y; p.A = a.z; p.B = a.w; p.C = b.x;
+    p.rx0 = rc.x & 0xFFFF; p.rx1 = rc.x >> 16; p.ry0 = rc.y & 0xFFFF; p.ry1 = rc.y >> 16;
+    qthr = b.w;
+    const int area = (p.rx1 - p.rx0) * (p.ry1 - p.ry0);
+    coop = exact_cull != 0 && area > kCoopTiles;
+    if (!coop) count_or_emit_tiles(p, qthr, W, H, gx, exact_cull != 0, bv.keys + off, bv.vals + off, i);
+  }
+  coop_count_or_emit(coop, p, qthr, W, H, gx, bv.keys + off, bv.vals + off, i);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1166,6 +1240,306 @@ k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
 }
 
 // ------------------------------------------------------------------------------------------
+// blend v3: 2 warps per tile, each warp owns an 8x16 block = four 8x4 quarters; every lane carries FOUR
+// pixels (x, y + 4q) sharing dx, processed as two packed f32x2 pairs.  One instruction stream serves 128
+// (pixel, Gaussian) pairs, so the per-Gaussian overheads (loop, slab reads, the 9-value warp reduction and
+// the REDs in the backward) are amortised over twice as many pairs as in v2.  Culling stays per 8x4 quarter.
+// ------------------------------------------------------------------------------------------
+constexpr int kThreads3 = 64;
+#ifndef GSB_FWD3_MINB
+#define GSB_FWD3_MINB 10
+#endif
+#ifndef GSB_BWD3_MINB
+#define GSB_BWD3_MINB 8
+#endif
+
+template <bool BULK>
+__global__ void __launch_bounds__(kThreads3, GSB_FWD3_MINB)
+k_blend_fwd3(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
+             const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+             float* __restrict__ out_color, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+  __shared__ __align__(128) SlabStage stg[BULK ? 2 : 1];
+  __shared__ __align__(8) uint64_t bars[2];
+  if (BULK) {
+    if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+  }
+  const int tile = blockIdx.x;
+  const int tx = tile % gx, ty = tile / gx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sx0 = tx * kBlock + warp * 8, sy0 = ty * kBlock;
+  const int px = sx0 + (lane & 7), py0 = sy0 + (lane >> 3);
+  const float fx = (float)px;
+  const float rx0 = (float)sx0, rx1 = (float)min(sx0 + 7, W - 1);
+  float2 fy[2];
+  bool in[4], done[4], wdone[4];
+  float ry0[4], ry1[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int py = py0 + 4 * q;
+    in[q] = px < W && py < H;
+    done[q] = !in[q];
+    wdone[q] = !(sx0 < W && sy0 + 4 * q < H);
+    ry0[q] = (float)(sy0 + 4 * q);
+    ry1[q] = (float)min(sy0 + 4 * q + 3, H - 1);
+  }
+  fy[0] = f2((float)py0, (float)(py0 + 4));
+  fy[1] = f2((float)(py0 + 8), (float)(py0 + 12));
+  const uint2 rg = ranges[tile];
+  const int n = (int)(rg.y - rg.x);
+  float2 T[2], Cr[2], Cg[2], Cb[2];
+  uint32_t last[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) { T[h] = f2(1.f, 1.f); Cr[h] = Cg[h] = Cb[h] = f2(0.f, 0.f); }
+  const int nch = (n + kChunk - 1) / kChunk;
+  if (BULK && nch > 0) stage_slab<true>(&stg[0], s0, s1, s2, (size_t)rg.x, min(kChunk, n), &bars[0], kThreads3);
+  int pending = -1;
+  for (int ci = 0; ci < nch; ++ci) {
+    const int base = ci * kChunk;
+    const int cnt = min(kChunk, n - base);
+    const SlabStage* cur = &stg[BULK ? (ci & 1) : 0];
+    if (BULK) {
+      pending = -1;
+      if (ci + 1 < nch) {
+        stage_slab<true>(&stg[(ci + 1) & 1], s0, s1, s2, (size_t)rg.x + base + kChunk, min(kChunk, n - base - kChunk),
+                         &bars[(ci + 1) & 1], kThreads3);
+        pending = ci + 1;
+      }
+      mbar_wait(&bars[ci & 1], (uint32_t)((ci >> 1) & 1));
+    } else {
+      stage_slab<false>(&stg[0], s0, s1, s2, (size_t)rg.x + base, cnt, nullptr, kThreads3);
+      __syncthreads();
+    }
+    const float4* sm0 = cur->s0;
+    const float4* sm1 = cur->s1;
+    const float4* sm2 = cur->s2;
+    bool wall = wdone[0] && wdone[1] && wdone[2] && wdone[3];
+    if (!wall) {
+      for (int b = 0; b < cnt; b += 32) {
+        const int j = b + lane;
+        bool hit = false;
+        if (j < cnt) {
+          const float4 e0 = sm0[j], e1 = sm1[j];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (!hit && !wdone[q]) hit = slab_may_contribute(e0, e1, rx0, ry0[q], rx1, ry1[q]);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+          const int k = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float4 e0 = sm0[b + k], e1 = sm1[b + k], c = sm2[b + k];
+          const float dx = e0.x - fx;
+          const float c1 = e0.w * dx, c0 = e0.z * dx * dx;
+          const uint32_t pos = (uint32_t)(base + b + k + 1);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float2 dy = f2(e0.y - fy[h].x, e0.y - fy[h].y);
+            const float2 pw = __ffma2_rn(dy, __ffma2_rn(f2s(e1.x), dy, f2s(c1)), f2s(c0));
+            const float2 G = f2(ex2_approx(pw.x), ex2_approx(pw.y));
+            float2 al = __fmul2_rn(f2s(e1.y), G);
+            al.x = fminf(0.99f, al.x); al.y = fminf(0.99f, al.y);
+            bool vA = !done[2 * h] && pw.x <= 0.f && al.x >= kAlphaMin;
+            bool vB = !done[2 * h + 1] && pw.y <= 0.f && al.y >= kAlphaMin;
+            const float2 tT = __fmul2_rn(T[h], __ffma2_rn(al, f2s(-1.f), f2s(1.f)));
+            if (vA && tT.x < kTEps) { done[2 * h] = true; vA = false; }
+            if (vB && tT.y < kTEps) { done[2 * h + 1] = true; vB = false; }
+            float2 w = __fmul2_rn(al, T[h]);
+            w.x = vA ? w.x : 0.f; w.y = vB ? w.y : 0.f;
+            Cr[h] = __ffma2_rn(f2s(c.x), w, Cr[h]);
+            Cg[h] = __ffma2_rn(f2s(c.y), w, Cg[h]);
+            Cb[h] = __ffma2_rn(f2s(c.z), w, Cb[h]);
+            T[h].x = vA ? tT.x : T[h].x; T[h].y = vB ? tT.y : T[h].y;
+            last[2 * h] = vA ? pos : last[2 * h]; last[2 * h + 1] = vB ? pos : last[2 * h + 1];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) wdone[q] = __all_sync(0xffffffffu, done[q]);
+        wall = wdone[0] && wdone[1] && wdone[2] && wdone[3];
+        if (wall) break;
+      }
+    }
+    if (__syncthreads_and(wall)) break;
+    pending = -1;
+  }
+  if (BULK && pending >= 0) mbar_wait(&bars[pending & 1], (uint32_t)((pending >> 1) & 1));
+  const size_t hw = (size_t)W * H;
+  const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (in[q]) {
+      const int h = q >> 1;
+      const float t = (q & 1) ? T[h].y : T[h].x;
+      const float r = (q & 1) ? Cr[h].y : Cr[h].x, g = (q & 1) ? Cg[h].y : Cg[h].x, bb = (q & 1) ? Cb[h].y : Cb[h].x;
+      const size_t pix = (size_t)(py0 + 4 * q) * W + px;
+      final_T[pix] = t; n_contrib[pix] = last[q];
+      out_color[pix] = r + t * b0; out_color[hw + pix] = g + t * b1; out_color[2 * hw + pix] = bb + t * b2;
+    }
+  }
+}
+
+template <bool BULK>
+__global__ void __launch_bounds__(kThreads3, GSB_BWD3_MINB)
+k_blend_bwd3(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
+             const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+             const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
+             const float* __restrict__ dL_dpix, float* __restrict__ dacc) {
+  __shared__ __align__(128) SlabStage stg[BULK ? 2 : 1];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ int s_bmax;
+  if (BULK && threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  const int tile = blockIdx.x;
+  const int tx = tile % gx, ty = tile / gx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sx0 = tx * kBlock + warp * 8, sy0 = ty * kBlock;
+  const int px = sx0 + (lane & 7), py0 = sy0 + (lane >> 3);
+  const float fx = (float)px;
+  const float rx0 = (float)sx0, rx1 = (float)min(sx0 + 7, W - 1);
+  const uint2 rg = ranges[tile];
+  const size_t hw = (size_t)W * H;
+  const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+  float2 fy[2], T[2], dLr[2], dLg[2], dLb[2], tf_bg[2], acc_r[2], acc_g[2], acc_b[2];
+  int lc[4], wmaxq[4];
+  float ry0[4], ry1[4];
+  bool in[4];
+  fy[0] = f2((float)py0, (float)(py0 + 4));
+  fy[1] = f2((float)(py0 + 8), (float)(py0 + 12));
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int py = py0 + 4 * q;
+    in[q] = px < W && py < H;
+    const size_t pix = (size_t)py * W + px;
+    const float tfin = in[q] ? final_T[pix] : 0.f;
+    lc[q] = in[q] ? (int)n_contrib[pix] : 0;
+    const float r = in[q] ? dL_dpix[pix] : 0.f, g = in[q] ? dL_dpix[hw + pix] : 0.f, bb = in[q] ? dL_dpix[2 * hw + pix] : 0.f;
+    const int h = q >> 1;
+    if (q & 1) { T[h].y = tfin; dLr[h].y = r; dLg[h].y = g; dLb[h].y = bb; tf_bg[h].y = tfin * (b0 * r + b1 * g + b2 * bb); }
+    else       { T[h].x = tfin; dLr[h].x = r; dLg[h].x = g; dLb[h].x = bb; tf_bg[h].x = tfin * (b0 * r + b1 * g + b2 * bb); }
+    ry0[q] = (float)(sy0 + 4 * q);
+    ry1[q] = (float)min(sy0 + 4 * q + 3, H - 1);
+    int m = lc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    wmaxq[q] = m;
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) acc_r[h] = acc_g[h] = acc_b[h] = f2(0.f, 0.f);
+  const int wmax = max(max(wmaxq[0], wmaxq[1]), max(wmaxq[2], wmaxq[3]));
+  if (threadIdx.x == 0) s_bmax = 0;
+  __syncthreads();
+  if (lane == 0) atomicMax(&s_bmax, wmax);
+  __syncthreads();
+  const int bmax = s_bmax;
+  const int nchunks = (bmax + kChunk - 1) / kChunk;
+  if (BULK && nchunks > 0)
+    stage_slab<true>(&stg[0], s0, s1, s2, (size_t)rg.x + (size_t)(nchunks - 1) * kChunk,
+                     min(kChunk, bmax - (nchunks - 1) * kChunk), &bars[0], kThreads3);
+  for (int it = 0; it < nchunks; ++it) {
+    const int ch = nchunks - 1 - it;
+    const int base = ch * kChunk;
+    const int cnt = min(kChunk, bmax - base);
+    const SlabStage* cur = &stg[BULK ? (it & 1) : 0];
+    if (BULK) {
+      if (it + 1 < nchunks)
+        stage_slab<true>(&stg[(it + 1) & 1], s0, s1, s2, (size_t)rg.x + base - kChunk, kChunk, &bars[(it + 1) & 1],
+                         kThreads3);
+      mbar_wait(&bars[it & 1], (uint32_t)((it >> 1) & 1));
+    } else {
+      stage_slab<false>(&stg[0], s0, s1, s2, (size_t)rg.x + base, cnt, nullptr, kThreads3);
+      __syncthreads();
+    }
+    const float4* sm0 = cur->s0;
+    const float4* sm1 = cur->s1;
+    const float4* sm2 = cur->s2;
+    if (base < wmax) {
+      for (int b = (cnt - 1) & ~31; b >= 0; b -= 32) {
+        if (base + b >= wmax) continue;
+        const int j = b + lane;
+        bool hit = false;
+        if (j < cnt) {
+          const float4 e0 = sm0[j], e1 = sm1[j];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (!hit && base + j < wmaxq[q]) hit = slab_may_contribute(e0, e1, rx0, ry0[q], rx1, ry1[q]);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+          const int k = 31 - __clz(mask);
+          mask &= ~(1u << k);
+          const int pos = base + b + k;
+          const float4 e0 = sm0[b + k], e1 = sm1[b + k];
+          const float dx = e0.x - fx;
+          const float c1 = e0.w * dx, c0 = e0.z * dx * dx;
+          float2 dy[2], G[2], al[2];
+          bool v[4];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            dy[h] = f2(e0.y - fy[h].x, e0.y - fy[h].y);
+            const float2 pw = __ffma2_rn(dy[h], __ffma2_rn(f2s(e1.x), dy[h], f2s(c1)), f2s(c0));
+            G[h] = f2(ex2_approx(pw.x), ex2_approx(pw.y));
+            al[h] = __fmul2_rn(f2s(e1.y), G[h]);
+            al[h].x = fminf(0.99f, al[h].x); al[h].y = fminf(0.99f, al[h].y);
+            v[2 * h] = in[2 * h] && pos < lc[2 * h] && pw.x <= 0.f && al[h].x >= kAlphaMin;
+            v[2 * h + 1] = in[2 * h + 1] && pos < lc[2 * h + 1] && pw.y <= 0.f && al[h].y >= kAlphaMin;
+          }
+          if (!__any_sync(0xffffffffu, v[0] || v[1] || v[2] || v[3])) continue;
+          const float4 c = sm2[b + k];
+          float s_u = 0.f, s_uy = 0.f, s_uyy = 0.f, s_do = 0.f, s_r = 0.f, s_g = 0.f, s_b = 0.f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float2 am = f2(v[2 * h] ? al[h].x : 0.f, v[2 * h + 1] ? al[h].y : 0.f);
+            const float2 one_m = __ffma2_rn(am, f2s(-1.f), f2s(1.f));
+            const float2 inv = f2(rcp_approx(one_m.x), rcp_approx(one_m.y));
+            T[h] = __fmul2_rn(T[h], inv);
+            const float2 dcol = __fmul2_rn(am, T[h]);
+            const float2 d_r = __fadd2_rn(f2s(c.x), f2(-acc_r[h].x, -acc_r[h].y));
+            const float2 d_g = __fadd2_rn(f2s(c.y), f2(-acc_g[h].x, -acc_g[h].y));
+            const float2 d_b = __fadd2_rn(f2s(c.z), f2(-acc_b[h].x, -acc_b[h].y));
+            float2 da = __ffma2_rn(d_b, dLb[h], __ffma2_rn(d_g, dLg[h], __fmul2_rn(d_r, dLr[h])));
+            da = __fmul2_rn(da, T[h]);
+            da = __ffma2_rn(f2(-tf_bg[h].x, -tf_bg[h].y), inv, da);
+            da.x = v[2 * h] ? da.x : 0.f; da.y = v[2 * h + 1] ? da.y : 0.f;
+            acc_r[h] = __ffma2_rn(am, d_r, acc_r[h]);
+            acc_g[h] = __ffma2_rn(am, d_g, acc_g[h]);
+            acc_b[h] = __ffma2_rn(am, d_b, acc_b[h]);
+            const float2 gda = __fmul2_rn(G[h], da);                 // G * dL/dalpha
+            const float2 u = __fmul2_rn(f2s(e1.y), gda);             // u = G * dL/dG = opacity * G * dL/dalpha
+            const float2 uy = __fmul2_rn(u, dy[h]);
+            const float2 uyy = __fmul2_rn(uy, dy[h]);
+            const float2 cr = __fmul2_rn(dcol, dLr[h]), cg = __fmul2_rn(dcol, dLg[h]), cb = __fmul2_rn(dcol, dLb[h]);
+            s_u += u.x + u.y; s_uy += uy.x + uy.y; s_uyy += uyy.x + uyy.y; s_do += gda.x + gda.y;
+            s_r += cr.x + cr.y; s_g += cg.x + cg.y; s_b += cb.x + cb.y;
+          }
+          // raw moments (dx is common to the lane's four pixels); the conic / ln2 factors are applied after the
+          // warp reduction by the two lanes that issue the REDs
+          float vv[9];
+          vv[0] = s_u * dx;            // S_x  = sum u dx
+          vv[1] = s_uy;                // S_y  = sum u dy
+          vv[2] = s_u * dx * dx;       // S_xx
+          vv[3] = s_uy * dx;           // S_xy
+          vv[4] = s_uyy;               // S_yy
+          vv[5] = s_do;
+          vv[6] = s_r; vv[7] = s_g; vv[8] = s_b;
+          warp_reduce9(vv, lane);
+          const float a1 = __shfl_down_sync(0xffffffffu, vv[0], 4);
+          const float a2 = __shfl_down_sync(0xffffffffu, vv[0], 8);
+          const float a3 = __shfl_down_sync(0xffffffffu, vv[0], 12);
+          float* dst = dacc + (size_t)__float_as_uint(e1.w) * 12;
+          if (lane == 0) {        // holds S_x, S_y, S_xx, S_xy
+            const float Sx = vv[0], Sy = a1;
+            red_add_v4(dst, kLn2 * (2.f * Sx * e0.z + Sy * e0.w), kLn2 * (2.f * Sy * e1.x + Sx * e0.w), -0.5f * a2, -a3);
+          } else if (lane == 16) {  // holds S_yy, do, r, g
+            red_add_v4(dst + 4, -0.5f * vv[0], a1, a2, a3);
+          }
+          if (lane == 1) atomicAdd(dst + 8, vv[8]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_preprocess_bwd
 // ------------------------------------------------------------------------------------------
 struct OutPtrs {
@@ -1282,25 +1656,35 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int* __restrict__ radii_unused, O
   }
 }
 
-__global__ void __launch_bounds__(256) k_pose_finalize(const float* part, int nblocks, const float* pose,
-                                                       float* dpose) {
-  __shared__ float s[16][17];
-  const int k = threadIdx.x & 15, g = threadIdx.x >> 4;   // 16 groups of 16
-  float v = 0.f;
-  for (int b = g; b < nblocks; b += 16) v += part[(size_t)b * 16 + k];
-  s[g][k] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float acc[16];
-    for (int c = 0; c < 16; ++c) {
-      float a = 0.f;
-      for (int r = 0; r < 16; ++r) a += s[r][c];
-      acc[c] = a;
-    }
-    float dp[7];
-    pose_grad_finalize(pose, acc, dp);
-    for (int c = 0; c < 7; ++c) dpose[c] = dp[c];
+// Pose-gradient partials [nblocks][16] -> 16 column sums (one CTA per column, deterministic order) ...
+__global__ void __launch_bounds__(256) k_pose_reduce(const float* __restrict__ part, int nblocks, float* __restrict__ acc16) {
+  __shared__ float s[256];
+  const int c = blockIdx.x;
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+  int b = threadIdx.x;
+  for (; b + 768 < nblocks; b += 1024) {
+    v0 += part[(size_t)b * 16 + c];
+    v1 += part[(size_t)(b + 256) * 16 + c];
+    v2 += part[(size_t)(b + 512) * 16 + c];
+    v3 += part[(size_t)(b + 768) * 16 + c];
   }
+  for (; b < nblocks; b += 256) v0 += part[(size_t)b * 16 + c];
+  s[threadIdx.x] = (v0 + v1) + (v2 + v3);
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) acc16[c] = s[0];
+}
+// ... and the chain to dL/dP[7] (utils/pose_utils.py quad2rotation + normalisation backward).
+__global__ void k_pose_finalize(const float* __restrict__ acc16, const float* pose, float* dpose) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float acc[16];
+  for (int c = 0; c < 16; ++c) acc[c] = acc16[c];
+  float dp[7];
+  pose_grad_finalize(pose, acc, dp);
+  for (int c = 0; c < 7; ++c) dpose[c] = dp[c];
 }
 
 __global__ void k_mark_visible(int P, const float* means, const float* V, uint8_t* present) {
@@ -1412,7 +1796,13 @@ extern "C" GSB_API int gsb_render(const GsbCamera* cam, int32_t P, void* geom, v
       k_ranges_gather<<<(unsigned)((R + kThreads - 1) / kThreads), kThreads, 0, st>>>((uint32_t)R, gv, bv); }
   }
   { ProfScope ps(GSB_K_BLEND_FWD, st);
-    if (g_blend_version == 2 && g_stage_bulk)
+    if (g_blend_version == 3 && g_stage_bulk)
+      k_blend_fwd3<true><<<gx * gy, kThreads3, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, out_color,
+                                                        iv.final_T, iv.n_contrib);
+    else if (g_blend_version == 3)
+      k_blend_fwd3<false><<<gx * gy, kThreads3, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, out_color,
+                                                         iv.final_T, iv.n_contrib);
+    else if (g_blend_version == 2 && g_stage_bulk)
       k_blend_fwd2<true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, out_color,
                                                         iv.final_T, iv.n_contrib);
     else if (g_blend_version == 2)
@@ -1447,7 +1837,13 @@ extern "C" GSB_API int gsb_backward(const GsbCamera* cam, const GsbGaussians* g,
   GSB_CUDA(cudaMemsetAsync(gv.dacc, 0, (size_t)P * 48, st));
   if (R > 0) {
     ProfScope ps(GSB_K_BLEND_BWD, st);
-    if (g_blend_version == 2 && g_stage_bulk)
+    if (g_blend_version == 3 && g_stage_bulk)
+      k_blend_bwd3<true><<<gx * gy, kThreads3, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, iv.final_T,
+                                                        iv.n_contrib, dL_dout, (float*)gv.dacc);
+    else if (g_blend_version == 3)
+      k_blend_bwd3<false><<<gx * gy, kThreads3, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, iv.final_T,
+                                                         iv.n_contrib, dL_dout, (float*)gv.dacc);
+    else if (g_blend_version == 2 && g_stage_bulk)
       k_blend_bwd2<true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, iv.final_T,
                                                         iv.n_contrib, dL_dout, (float*)gv.dacc);
     else if (g_blend_version == 2)
@@ -1465,9 +1861,12 @@ extern "C" GSB_API int gsb_backward(const GsbCamera* cam, const GsbGaussians* g,
                 (uintptr_t)out.dsh_dc | (uintptr_t)out.dsh_rest;
   if (a & 15) in.vec_ok = 0;
   const int nb = (P + kPT - 1) / kPT;
-  { ProfScope ps(GSB_K_PREPROCESS_BWD, st, g->pose ? 2 : 1);
+  { ProfScope ps(GSB_K_PREPROCESS_BWD, st, g->pose ? 3 : 1);
     k_preprocess_bwd<<<nb, kPT, kPrepSmem, st>>>(in, gv, nullptr, out);
-    if (g->pose) k_pose_finalize<<<1, 256, 0, st>>>(gv.pose_part, nb, g->pose, grads->dL_dpose); }
+    if (g->pose) {
+      k_pose_reduce<<<16, 256, 0, st>>>(gv.pose_part, nb, gv.pose_acc);
+      k_pose_finalize<<<1, 32, 0, st>>>(gv.pose_acc, g->pose, grads->dL_dpose);
+    } }
   GSB_CUDA(cudaGetLastError());
   return GSB_OK;
 }

@@ -225,26 +225,32 @@ def test_exact_cull_is_lossless():
 
 
 def test_blend_kernel_versions_agree():
-    """v1 (one pixel per lane) and v2 (two pixels per lane, packed f32x2) blend kernels."""
+    """v1 (one pixel per lane), v2 (two pixels, packed f32x2) and v3 (four pixels) blend kernels, with and
+    without TMA bulk staging, on a scene whose image size is not a multiple of the tile size."""
     import instantsplat_b200 as I
     L = I.lib()
     sc = surface_scene(40_000, 3, 300, 200, seed=17, sh_degree=2)
     bg = torch.tensor([0.1, 0.0, 0.2])
     gt = torch.rand(3, sc.height, sc.width, generator=torch.Generator().manual_seed(3))
+    res = {}
     try:
-        assert L.gsb_set_option(b"blend_version", 1) == 0
-        a_img, a_r, a_loss, a_g = cuda_run(sc, 2, bg, gt)
-        assert L.gsb_set_option(b"blend_version", 2) == 0
-        b_img, b_r, b_loss, b_g = cuda_run(sc, 2, bg, gt)
+        for ver, bulk in ((1, 0), (2, 1), (2, 0), (3, 1), (3, 0)):
+            assert L.gsb_set_option(b"blend_version", ver) == 0 and L.gsb_set_option(b"stage_bulk", bulk) == 0
+            res[(ver, bulk)] = cuda_run(sc, 2, bg, gt)
     finally:
         L.gsb_set_option(b"blend_version", 2)
+        L.gsb_set_option(b"stage_bulk", 1)
     assert L.gsb_set_option(b"blend_version", 7) != 0 and L.gsb_set_option(b"nope", 1) != 0
-    assert torch.equal(a_r, b_r)
-    # the two versions round alpha differently, so an occasional 1/255-threshold flip is legitimate
-    d = (a_img - b_img).abs().max(0)[0]
-    assert float((d > 1e-5).float().mean()) < 1e-4 and float(d.max()) < 5e-3
-    for k in NAMES + ("pose", "means2D"):
-        assert rel_err(b_g[k], a_g[k]) < 5e-3, k
+    a_img, a_r, a_loss, a_g = res[(1, 0)]
+    for key, (b_img, b_r, b_loss, b_g) in res.items():
+        assert torch.equal(a_r, b_r), key
+        # the versions round alpha differently, so an occasional 1/255-threshold flip is legitimate
+        d = (a_img - b_img).abs().max(0)[0]
+        assert float((d > 1e-5).float().mean()) < 1e-4 and float(d.max()) < 5e-3, key
+        for k in NAMES + ("pose", "means2D"):
+            assert rel_err(b_g[k], a_g[k]) < 5e-3, (key, k)
+    # bulk vs cooperative staging of the same version must agree exactly in the forward
+    assert torch.equal(res[(3, 1)][0], res[(3, 0)][0]) and torch.equal(res[(2, 1)][0], res[(2, 0)][0])
 
 
 def test_generic_boundary_b2_nonidentity_view_packed_sh():

@@ -109,9 +109,10 @@ def measured_peaks():
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the path on the host cores, on a bounded sample of the workload
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_step(sc, view, gt, n_gauss, tiles, threads):
+def cpu_reference_step(sc, view, gt, n_gauss, tiles, threads, loss_rows=None):
     """One sampled iteration of the oracle.  Returns seconds for (projection fwd+bwd over n_gauss
-    Gaussians, blend fwd+bwd over `tiles`, loss fwd+bwd on the full image, per-point Adam on n_gauss)."""
+    Gaussians, blend fwd+bwd over `tiles`, loss fwd+bwd on the first `loss_rows` image rows, per-point Adam
+    on n_gauss)."""
     from oracle import gs_oracle as O
     torch.set_num_threads(threads)
     cam = O.Camera.instantsplat(sc.width, sc.height, sc.fovx, sc.fovy, sh_degree=sc.sh_degree)
@@ -127,8 +128,9 @@ def cpu_reference_step(sc, view, gt, n_gauss, tiles, threads):
     if img.requires_grad:
         (img * torch.ones_like(img)).sum().backward()
     t2 = time.perf_counter()
-    im = img.detach().clone().requires_grad_(True)
-    O.training_loss(im, gt).backward()
+    rows = sc.height if loss_rows is None else loss_rows
+    im = img.detach()[:, :rows].clone().requires_grad_(True)
+    O.training_loss(im, gt[:, :rows]).backward()
     t3 = time.perf_counter()
     for k, p in prm.items():
         g = p.grad if p.grad is not None else torch.zeros_like(p)
@@ -138,32 +140,36 @@ def cpu_reference_step(sc, view, gt, n_gauss, tiles, threads):
 
 
 def cpu_arm(sc, steps, warmup, budget_s):
-    """Returns dict(value iters/s extrapolated to the full workload, sample description, cores)."""
+    """Returns dict(value iters/s extrapolated to the full workload, sample description, cores).  Every step is a
+    bounded SAMPLE of one iteration: a subset of the Gaussians (projection + Adam), of the tiles (blend) and of the
+    image rows (loss), each extrapolated linearly to the full iteration, sized so that all steps fit `budget_s`."""
     threads = min(os.cpu_count() or 1, 32)   # more threads only add sync overhead on these op sizes
     gx, gy = (sc.width + 15) // 16, (sc.height + 15) // 16
     T = gx * gy
     gt = torch.rand(3, sc.height, sc.width, generator=torch.Generator().manual_seed(0))
     # probe with a very small sample, then size the sample to the budget
-    n_g, n_t = min(sc.P, 50_000), 4
-    centre = [(gy // 2) * gx + gx // 2 + i for i in range(-2, 2)]
-    tp, tb, tl, ta = cpu_reference_step(sc, 0, gt, n_g, centre[:n_t], threads)
-    per_g, per_t = (tp + ta) / n_g, max(tb, 1e-3) / n_t
+    n_g, n_t, rows = min(sc.P, 20_000), 2, min(sc.height, 64)
+    centre = [(gy // 2) * gx + gx // 2 + i for i in range(-1, 1)]
+    tp, tb, tl, ta = cpu_reference_step(sc, 0, gt, n_g, centre[:n_t], threads, rows)
+    per_g, per_t, per_row = (tp + ta) / n_g, max(tb, 1e-3) / n_t, max(tl, 1e-3) / rows   # per_t at the probe's n_g
     total_steps = max(1, steps + warmup)
-    per_step_budget = max(0.5, budget_s / total_steps - tl)
-    n_g = int(max(10_000, min(sc.P, 0.5 * per_step_budget / per_g)))
-    n_t = int(max(2, min(T, 0.5 * per_step_budget / per_t)))
+    per_step_budget = max(0.05, budget_s / total_steps)
+    n_g = int(max(2_000, min(sc.P, 0.35 * per_step_budget / per_g)))
+    n_t = int(max(1, min(T, 0.35 * per_step_budget / per_t)))
+    rows = int(max(32, min(sc.height, 0.3 * per_step_budget / per_row)))
     stride = max(1, T // n_t)
     tiles = list(range(stride // 2, T, stride))[:n_t]
     times = []
     for s in range(total_steps):
-        tp, tb, tl, ta = cpu_reference_step(sc, s % sc.n_views, gt, n_g, tiles, threads)
+        tp, tb, tl, ta = cpu_reference_step(sc, s % sc.n_views, gt, n_g, tiles, threads, rows)
         if s >= warmup:
-            times.append((tp + ta) * (sc.P / n_g) + tb * (T / len(tiles)) + tl)
+            # tile lists are built from the sampled Gaussians only, so blend time scales with both ratios
+            times.append((tp + ta) * (sc.P / n_g) + tb * (T / len(tiles)) * (sc.P / n_g) + tl * (sc.height / rows))
     est = sum(times) / len(times)
     return dict(value=1.0 / est, unit=UNIT, cores=threads, kind="port",
-                sample=(f"oracle/gs_oracle.py (PyTorch CPU, {threads} threads): projection fwd+bwd and Adam on "
-                        f"{n_g} of {sc.P} Gaussians, blend fwd+bwd on {len(tiles)} of {T} tiles (both extrapolated "
-                        f"linearly), L1+SSIM fwd+bwd on the full image; {len(times)} timed steps"),
+                sample=(f"oracle/gs_oracle.py (PyTorch CPU, {threads} threads): per step projection fwd+bwd and Adam on "
+                        f"{n_g} of {sc.P} Gaussians, blend fwd+bwd of those Gaussians on {len(tiles)} of {T} tiles, L1+SSIM fwd+bwd on "
+                        f"{rows} of {sc.height} image rows, each extrapolated linearly; {len(times)} timed steps"),
                 sec_per_iter_extrapolated=est)
 
 

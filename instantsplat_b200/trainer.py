@@ -102,6 +102,7 @@ class JointTrainer:
             self.exp_avg = torch.zeros(n_sh, dtype=torch.float32, device=self.dev)
             self.exp_avg_sq = torch.zeros(n_sh, dtype=torch.float32, device=self.dev)
             self._sync = torch.zeros(1, dtype=torch.float32, device=self.dev)
+            self._xch = torch.zeros(8 + scene.n_views * 7, dtype=torch.float32, device=self.dev)
         else:
             self.params = torch.zeros(total, dtype=torch.float32, device=self.dev)
             self.grads = torch.zeros(total, dtype=torch.float32, device=self.dev)
@@ -110,7 +111,8 @@ class JointTrainer:
         for name, k in SEGMENTS:
             self.view(self.params, name).copy_(scene.params[name].reshape(P, k).to(self.dev))
         self.poses = scene.poses.to(self.dev).float().contiguous()              # [n_views,7]
-        self.pose_grad = torch.zeros_like(self.poses)
+        self.pose_grad = (self._xch[8:].view(scene.n_views, 7) if self.exchange == "fused_p2p"
+                          else torch.zeros_like(self.poses))
         self.pose_m = torch.zeros_like(self.poses)
         self.pose_v = torch.zeros_like(self.poses)
         self.per_point_lr = None
@@ -291,8 +293,11 @@ class JointTrainer:
             a.numel, a.row_len, a.grad_scale = g.numel(), k, 1.0
             a.step_size, a.beta1, a.beta2, a.eps, a.weight_decay = 0.0, b1, b2, eps, 0.0
         check(L.gsb_adam_gate(len(SEGMENTS), arr, self.flags.data_ptr(), st), "gsb_adam_gate")
-        dist.all_reduce(self.flags, op=dist.ReduceOp.MAX, group=self.pg)
-        dist.all_reduce(self.pose_grad, op=dist.ReduceOp.SUM, group=self.pg)
+        # one small SUM all-reduce carries both the gate flags (as counts) and the pose-gradient table
+        # (self.pose_grad is a view of self._xch[8:]); it is also the pre-barrier of the fused kernel
+        self._xch[:8].copy_(self.flags)
+        dist.all_reduce(self._xch, op=dist.ReduceOp.SUM, group=self.pg)
+        self.flags.copy_(self._xch[:8])
         # 2. the fused kernel over this rank's shard
         lo, hi = self.shard
         pieces = []

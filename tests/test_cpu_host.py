@@ -120,3 +120,29 @@ def test_gloo_world2_gradient_exchange(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_shard_bounds_cover_and_align():
+    from instantsplat_b200.parallel import shard_bounds
+    total = 59_000_123
+    edges = [shard_bounds(total, 8, r) for r in range(8)]
+    assert edges[0][0] == 0 and edges[-1][1] == total
+    for (a, b), (c, d) in zip(edges[:-1], edges[1:]):
+        assert b == c and a % 768 == 0 and c % 768 == 0
+    assert shard_bounds(100, 4, 3) == (100, 100)          # tiny buffer: trailing shards are empty
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) works without a GPU and prints exactly
+    one JSON line on stdout with the contract keys."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--scale", "0.01",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "cpu_baseline", "e2e", "config"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0

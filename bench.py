@@ -298,6 +298,34 @@ def run_b200(args):
     for s in range(2):
         e2e_step(W_ + K + s)
     ms_e2e = timed(e2e_step, K, W_ + K + 2)
+    # ---- the same iteration through the reference-shaped drop-in boundary (what an unchanged train.py calls):
+    # render() -> l1 + fused_ssim -> loss.backward() -> PerPointAdam.step() -> zero_grad, with torch autograd
+    dropin = None
+    if world == 1:
+        from instantsplat_b200.camera import SimpleCamera
+        pc = I.SimpleGaussianModel(sc, dev)
+        opt = pc.training_setup_pp()
+        camv = SimpleCamera(sc.width, sc.height, sc.fovx, sc.fovy, device=dev)
+        pipe = I.PipelineDefaults()
+        bgz = torch.zeros(3, device=dev)
+
+        def dropin_step(s):
+            v = s % sc.n_views
+            pkg = I.render(camv, pc, pipe, bgz, camera_pose=pc.get_RT(v))
+            img = pkg["render"]
+            gtv = gt_dev[v]
+            loss = 0.8 * torch.abs(img - gtv).mean() + 0.2 * (1.0 - I.fused_ssim(img.unsqueeze(0), gtv.unsqueeze(0)))
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+
+        nd = min(K, 50)
+        for s in range(3):
+            dropin_step(s)
+        ms_drop = timed(dropin_step, nd, 3)
+        dropin = {"value": nd / (ms_drop / 1e3), "unit": UNIT, "ms_per_step": ms_drop / nd, "steps": nd,
+                  "api": "instantsplat_b200.render() + torch l1 + fused_ssim + loss.backward() + PerPointAdam.step()"}
+        del pc, opt
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -355,7 +383,7 @@ def run_b200(args):
                 "api": "JointTrainer.step(view, gt=<pinned host image, H2D on a copy stream, double buffered>) + "
                        "loss_value() D2H every step"},
         "gpu_launches": launches, "gpu_launches_note": "libgsb200.so kernels only (cub sort/scan launches excluded)",
-        "kernels": kernels, "roofline": roof, "clocks": clocks, "cpu_baseline": cpu_base, "impl": "b200",
+        "dropin_boundary": dropin, "kernels": kernels, "roofline": roof, "clocks": clocks, "cpu_baseline": cpu_base, "impl": "b200",
     }
     if world > 1:
         dist.destroy_process_group()

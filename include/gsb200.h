@@ -185,6 +185,12 @@ GSB_API int gsb_fused_rs_adam_ag(int32_t world, int32_t rank, const float* const
                                  int64_t shard_begin, int32_t n_pieces, const GsbShardPiece* pieces,
                                  const uint32_t* flags, float grad_scale, gsb_stream_t stream);
 
+/* simple_knn._C.distCUDA2 (scene/gaussian_model.py:20,156-160; init only):
+ * out[i] = mean squared distance from point i to its 3 nearest neighbours (exact).  points [P,3], out [P]. */
+GSB_API size_t gsb_knn_scratch_bytes(int32_t P);
+GSB_API int gsb_knn_mean_dist2(int32_t P, const float* points, float* out, void* scratch, size_t scratch_bytes,
+                               gsb_stream_t stream);
+
 /* Optional instrumentation (bench.py): per-kernel CUDA-event timing on the launching stream and a
  * count of this library's own kernel launches (cub launches are not counted). */
 enum {

@@ -62,7 +62,8 @@ EXPORTS = ("gsb_geom_bytes", "gsb_binning_bytes", "gsb_image_bytes", "gsb_prepro
            "gsb_backward", "gsb_mark_visible", "gsb_ssim_forward", "gsb_ssim_backward",
            "gsb_loss_forward", "gsb_loss_backward", "gsb_adam_step", "gsb_last_error",
            "gsb_abi_version", "gsb_profile_enable", "gsb_profile_collect", "gsb_launch_count", "gsb_set_option", "gsb_adam_gate",
-           "gsb_ipc_alloc", "gsb_ipc_open", "gsb_ipc_close", "gsb_ipc_free", "gsb_fused_rs_adam_ag")
+           "gsb_ipc_alloc", "gsb_ipc_open", "gsb_ipc_close", "gsb_ipc_free", "gsb_fused_rs_adam_ag",
+           "gsb_knn_scratch_bytes", "gsb_knn_mean_dist2")
 KERNEL_IDS = ("preprocess", "sort_depth", "scan", "duplicate", "sort_tile", "gather", "blend_fwd", "blend_bwd",
               "preprocess_bwd", "loss_fwd", "loss_bwd", "adam")
 
@@ -124,6 +125,10 @@ def lib() -> ctypes.CDLL:
     L.gsb_ipc_free.argtypes = [vp]
     L.gsb_fused_rs_adam_ag.argtypes = [i32, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp, i64, i32,
                                        ctypes.POINTER(GsbShardPiece), vp, ctypes.c_float, vp]
+    L.gsb_knn_scratch_bytes.argtypes = [i32]
+    L.gsb_knn_scratch_bytes.restype = sz
+    L.gsb_knn_mean_dist2.argtypes = [i32, vp, vp, vp, sz, vp]
+    L.gsb_knn_mean_dist2.restype = ctypes.c_int
     for f in ("gsb_adam_gate", "gsb_ipc_alloc", "gsb_ipc_open", "gsb_ipc_close", "gsb_ipc_free",
               "gsb_fused_rs_adam_ag"):
         getattr(L, f).restype = ctypes.c_int

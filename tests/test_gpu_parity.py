@@ -577,3 +577,23 @@ def test_full_size_properties_1080p():
     finally:
         R.EXACT_CULL = True
     assert float((img3 - img1).abs().max()) <= 1e-6 and torch.equal(r3, r1)
+
+
+def test_knn_distcuda2_matches_bruteforce():
+    """shims/simple_knn distCUDA2 (grid-hash exact 3-NN) vs brute force, on a surface cloud, a uniform cloud,
+    a cloud with duplicates / far outliers, and tiny inputs."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "shims"))
+    from simple_knn._C import distCUDA2
+    g = torch.Generator().manual_seed(0)
+    clouds = [surface_scene(6000, 3, 64, 64, seed=3).params["xyz"], torch.rand(5000, 3, generator=g) * 4 - 2]
+    c = torch.randn(3000, 3, generator=g)
+    c[:50] = c[50:100]                      # exact duplicates
+    c[100] = torch.tensor([50.0, -40.0, 30.0])   # far outlier
+    clouds.append(c)
+    clouds += [torch.randn(7, 3, generator=g), torch.randn(4, 3, generator=g)]
+    for pts in clouds:
+        d = torch.cdist(pts.double(), pts.double())
+        ref = (d * d).topk(4, dim=1, largest=False).values[:, 1:].mean(dim=1).float()
+        got = distCUDA2(pts.to(DEV)).cpu()
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-7), float((got - ref).abs().max())

@@ -173,6 +173,59 @@ def cpu_arm(sc, steps, warmup, budget_s):
                 sec_per_iter_extrapolated=est)
 
 
+def gpu_torch_pieces(sc, dev, img, gt, reps=10):
+    """BASELINE.md row B-ref-py: the reference's Python-side pieces of the path (pose pre-transform + activations +
+    feature cat, l1 + PyTorch ssim, PerPointAdam), restated in oracle/gs_oracle.py, run with plain torch ops on
+    the SAME GPU -- what the fused preprocess / loss / Adam kernels replace.  Baseline leg only."""
+    from oracle import gs_oracle as O
+
+    def clock(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    prm = {k: v.to(dev).clone().requires_grad_(True) for k, v in sc.params.items()}
+    pose = sc.poses[0].to(dev).clone().requires_grad_(True)
+
+    def pre():
+        means, rots = O.pose_pretransform(prm["xyz"], prm["rotation"], pose)
+        shs = torch.cat([prm["f_dc"], prm["f_rest"]], dim=1)
+        out = means.sum() + rots.sum() + torch.exp(prm["scaling"]).sum() + torch.sigmoid(prm["opacity"]).sum() + shs.sum()
+        out.backward()
+        for p in list(prm.values()) + [pose]:
+            p.grad = None
+
+    im = img.detach().clone().requires_grad_(True)
+
+    def loss():
+        O.training_loss(im, gt).backward()
+        im.grad = None
+
+    ps = [v.detach().clone() for v in prm.values()]
+    gs_ = [torch.randn_like(p) * 1e-3 for p in ps]
+    ms = [torch.zeros_like(p) for p in ps]
+    vs = [torch.zeros_like(p) for p in ps]
+    ppl = sc.per_point_lr.to(dev) if sc.per_point_lr is not None else None
+    state = {"t": 0}
+
+    def adam():
+        state["t"] += 1
+        for i, p in enumerate(ps):
+            O.per_point_adam_step(p, gs_[i], ms[i], vs[i], state["t"], 1e-3, per_point_lr=ppl if i == 0 else None)
+
+    return {"pose_pretransform_activations_cat_fwd_bwd_ms": clock(pre), "l1_ssim_fwd_bwd_ms": clock(loss),
+            "per_point_adam_ms": clock(adam),
+            "what": "torch restatement (oracle/gs_oracle.py) of /root/reference/gaussian_renderer/__init__.py:81-92,102,121, "
+                    "utils/loss_utils.py:39-85 and scene/per_point_adam.py:34-98 run on the same GPU"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -361,6 +414,15 @@ def run_b200(args):
             "note": "algorithmic bytes = SURVEY.md 8(d) formulas with the measured R; the blend kernels are "
                     "bound by FP32/MUFU issue on (pixel,Gaussian) pairs, not by HBM (see DESIGN.md)"}
     t_render = sum(kernels[k]["ms"] for k in kernels if k not in ("loss_fwd", "loss_bwd", "adam"))
+    torch_pieces = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            torch_pieces = gpu_torch_pieces(sc, dev, tr.color, gt_dev[0])
+            torch_pieces["ours_ms"] = {"preprocess_fwd+bwd (whole kernels, incl. EWA/SH)": kernels["preprocess"]["ms"] + kernels["preprocess_bwd"]["ms"],
+                                       "loss_fwd+bwd": kernels["loss_fwd"]["ms"] + kernels["loss_bwd"]["ms"],
+                                       "adam": kernels["adam"]["ms"]}
+        except Exception as e:
+            torch_pieces = {"error": f"{type(e).__name__}: {e}"}
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -383,7 +445,7 @@ def run_b200(args):
                 "api": "JointTrainer.step(view, gt=<pinned host image, H2D on a copy stream, double buffered>) + "
                        "loss_value() D2H every step"},
         "gpu_launches": launches, "gpu_launches_note": "libgsb200.so kernels only (cub sort/scan launches excluded)",
-        "dropin_boundary": dropin, "kernels": kernels, "roofline": roof, "clocks": clocks, "cpu_baseline": cpu_base, "impl": "b200",
+        "dropin_boundary": dropin, "ref_python_pieces_gpu": torch_pieces, "kernels": kernels, "roofline": roof, "clocks": clocks, "cpu_baseline": cpu_base, "impl": "b200",
     }
     if world > 1:
         dist.destroy_process_group()

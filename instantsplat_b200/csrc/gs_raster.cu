@@ -1209,35 +1209,28 @@ k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
           acc_r = __ffma2_rn(am, d_r, acc_r);
           acc_g = __ffma2_rn(am, d_g, acc_g);
           acc_b = __ffma2_rn(am, d_b, acc_b);
-          const float2 gda = __fmul2_rn(G, da);                   // G * dL/dalpha
-          const float2 u = __fmul2_rn(f2s(e1.y), gda);            // u = G * dL/dG = opacity * G * dL/dalpha
-          const float2 uy = __fmul2_rn(u, dy);
-          const float2 uyy = __fmul2_rn(uy, dy);
-          const float2 cr = __fmul2_rn(dcol, dLr), cg = __fmul2_rn(dcol, dLg), cb = __fmul2_rn(dcol, dLb);
-          const float s_u = u.x + u.y, s_uy = uy.x + uy.y;
-          // raw moments (dx is common to the lane's two pixels); the conic / ln2 / -0.5 factors are applied AFTER
-          // the warp reduction by the two lanes that issue the REDs
+          const float2 dG = __fmul2_rn(f2s(e1.y), da);           // dL/dG = opacity * dL/dalpha
+          const float2 gdG = __fmul2_rn(G, dG);                  // G * dL/dG
+          const float2 gy = __fmul2_rn(gdG, dy);                 // G dL/dG dy
+          const float gxs = (gdG.x + gdG.y) * dx;                // sum over the two pixels of G dL/dG dx
+          const float gys = gy.x + gy.y;
           float v[9];
-          v[0] = s_u * dx;            // S_x  = sum u dx
-          v[1] = s_uy;                // S_y  = sum u dy
-          v[2] = s_u * dx * dx;       // S_xx
-          v[3] = s_uy * dx;           // S_xy
-          v[4] = uyy.x + uyy.y;       // S_yy
-          v[5] = gda.x + gda.y;       // dL/dopacity
-          v[6] = cr.x + cr.y;
-          v[7] = cg.x + cg.y;
-          v[8] = cb.x + cb.y;
+          v[0] = kLn2 * (2.f * gxs * e0.z + gys * e0.w);
+          v[1] = kLn2 * (2.f * gys * e1.x + gxs * e0.w);
+          v[2] = -0.5f * gxs * dx;
+          v[3] = -dx * gys;
+          v[4] = -0.5f * (gy.x * dy.x + gy.y * dy.y);
+          v[5] = G.x * da.x + G.y * da.y;
+          const float dcs_r = dcol.x * dLr.x + dcol.y * dLr.y;
+          v[6] = dcs_r;
+          v[7] = dcol.x * dLg.x + dcol.y * dLg.y;
+          v[8] = dcol.x * dLb.x + dcol.y * dLb.y;
           warp_reduce9(v, lane);
           const float a1 = __shfl_down_sync(0xffffffffu, v[0], 4);
           const float a2 = __shfl_down_sync(0xffffffffu, v[0], 8);
           const float a3 = __shfl_down_sync(0xffffffffu, v[0], 12);
           float* dst = dacc + (size_t)__float_as_uint(e1.w) * 12;
-          if (lane == 0) {          // holds S_x, S_y, S_xx, S_xy;  -A = 2 ln2 A', -B = ln2 B', -C = 2 ln2 C'
-            const float Sx = v[0], Sy = a1;
-            red_add_v4(dst, kLn2 * (2.f * Sx * e0.z + Sy * e0.w), kLn2 * (2.f * Sy * e1.x + Sx * e0.w), -0.5f * a2, -a3);
-          } else if (lane == 16) {  // holds S_yy, dL/dopacity, r, g
-            red_add_v4(dst + 4, -0.5f * v[0], a1, a2, a3);
-          }
+          if ((lane & 15) == 0) red_add_v4(dst + (lane >> 2), v[0], a1, a2, a3);
           if (lane == 1) atomicAdd(dst + 8, v[8]);
         }
       }

@@ -122,7 +122,7 @@ def pose_to_w2c(pose: torch.Tensor) -> torch.Tensor:
     """/root/reference/utils/pose_utils.py:57-84.  pose = [qw,qx,qy,qz,tx,ty,tz] -> 4x4."""
     R = quad2rotation(pose[:4])
     top = torch.cat([R, pose[4:7].reshape(3, 1)], dim=1)
-    bottom = torch.tensor([[0.0, 0.0, 0.0, 1.0]], dtype=pose.dtype)
+    bottom = torch.tensor([[0.0, 0.0, 0.0, 1.0]], dtype=pose.dtype, device=pose.device)
     return torch.cat([top, bottom], dim=0)
 
 
@@ -140,7 +140,7 @@ def quadmultiply(q1: torch.Tensor, q2: torch.Tensor) -> torch.Tensor:
 def pose_pretransform(xyz: torch.Tensor, rot: torch.Tensor, pose: torch.Tensor):
     """/root/reference/gaussian_renderer/__init__.py:81-89."""
     w2c = pose_to_w2c(pose)
-    homo = torch.cat([xyz, torch.ones(xyz.shape[0], 1, dtype=xyz.dtype)], dim=1)
+    homo = torch.cat([xyz, torch.ones(xyz.shape[0], 1, dtype=xyz.dtype, device=xyz.device)], dim=1)
     means = (w2c @ homo.t()).t()[:, :3]
     rots = quadmultiply(pose[:4], rot)
     return means, rots
@@ -445,7 +445,7 @@ def ssim_map(img1, img2, window_size=11):
     if squeeze:
         img1, img2 = img1[None], img2[None]
     ch = img1.shape[1]
-    g = gaussian_window(window_size, 1.5, img1.dtype)
+    g = gaussian_window(window_size, 1.5, img1.dtype).to(img1.device)
     w2 = (g[:, None] @ g[None, :])[None, None].expand(ch, 1, window_size, window_size).contiguous()
     pad = window_size // 2
     mu1 = F.conv2d(img1, w2, padding=pad, groups=ch)

@@ -17,15 +17,13 @@ lines = [f"# ncu `--set full --clock-control none` summaries, tag {tag}", "",
          "Workload: profiles/prof_step.py = 3 JointTrainer steps on BASELINE configs[2] (1M Gaussians, 1920x1080, SH 3); the 3rd",
          "launch of each kernel is captured.  Times under ncu are cold-cache and serialised (compare shares, not absolutes).", ""]
 traffic = {}
-if os.path.exists('profiles/traffic.json'):
-    traffic = json.load(open('profiles/traffic.json'))
 for rep in sorted(glob.glob(f'gpurun_out/{tag}_k_*.ncu-rep')):
     txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     if len(rows) < 3:
         continue
     hdr, units, vals = rows[0], rows[1], rows[-1]
-    kname = vals[hdr.index('Kernel Name')].split('(')[0].replace('<unnamed>::', '')
+    kname = vals[hdr.index('Kernel Name')].split('(')[0].replace('<unnamed>::', '').replace('void ', '').strip()
     lines += [f"## {kname}", "| metric | value | unit |", "|---|---|---|"]
     d = {}
     for w in WANT:

@@ -33,14 +33,30 @@ def launch_adam(entries, flags):
         check(L.gsb_adam_step(len(chunk), arr, flags.data_ptr(), _lib.stream_ptr()), "gsb_adam_step")
 
 
+def _validated_multiplier(param: torch.Tensor, mult):
+    """Type / device / shape checks of the optional per-row learning-rate multiplier; same exception types and
+    conditions as the reference optimizer (/root/reference/scene/per_point_adam.py:85-92)."""
+    if mult is None:
+        return None, 1
+    if not isinstance(mult, torch.Tensor):
+        raise TypeError("per_point_lr must be a torch.Tensor")
+    if mult.device != param.device:
+        raise ValueError("per_point_lr must be on the same device as parameter")
+    want = param.shape[:1] + (1,) * (param.dim() - 1)
+    if mult.shape != want:
+        raise ValueError(f"Invalid per_point_lr shape. Expected {want}, got {mult.shape}")
+    return mult.float().contiguous(), param.numel() // max(1, param.shape[0])
+
+
 class PerPointAdam(Optimizer):
+    """Adam with an optional per-point learning-rate multiplier (see module docstring)."""
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0):
-        if not all(0.0 <= x for x in [lr, eps, weight_decay]):
+        if min(lr, eps, weight_decay) < 0.0:
             raise ValueError(f"Invalid learning parameters: lr={lr}, eps={eps}, weight_decay={weight_decay}")
-        if not all(0.0 <= beta < 1.0 for beta in betas):
+        if any(not (0.0 <= b < 1.0) for b in betas):
             raise ValueError(f"Invalid beta parameters: {betas}")
-        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, per_point_lr=None)
-        super().__init__(params, defaults)
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, per_point_lr=None))
         self._flags = None
 
     @torch.no_grad()
@@ -49,47 +65,35 @@ class PerPointAdam(Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        entries = []
+        work = []
         for group in self.param_groups:
-            per_point_lr = group.get("per_point_lr")
-            beta1, beta2 = group["betas"]
+            b1, b2 = group["betas"]
             for p in group["params"]:
-                if p.grad is None:
+                g = p.grad
+                if g is None:
                     continue
-                grad = p.grad
-                if grad.is_sparse:
+                if g.is_sparse:
                     raise RuntimeError("PerPointAdam does not support sparse gradients")
                 if not p.is_cuda:
                     raise _lib.GsbError("PerPointAdam (B200) needs CUDA parameters; there is no CPU path")
-                state = self.state[p]
-                if len(state) == 0:
-                    state["step"] = 0
-                    state["exp_avg"] = torch.zeros_like(p)
-                    state["exp_avg_sq"] = torch.zeros_like(p)
-                state["step"] += 1
-                bc1 = 1 - beta1 ** state["step"]
-                bc2 = 1 - beta2 ** state["step"]
-                step_size = group["lr"] * (bc2 ** 0.5 / bc1)
-                row_len = 1
-                ppl = None
-                if per_point_lr is not None:
-                    if not isinstance(per_point_lr, torch.Tensor):
-                        raise TypeError("per_point_lr must be a torch.Tensor")
-                    if per_point_lr.device != p.device:
-                        raise ValueError("per_point_lr must be on the same device as parameter")
-                    expected_shape = p.shape[:1] + (1,) * (p.dim() - 1)
-                    if per_point_lr.shape != expected_shape:
-                        raise ValueError(f"Invalid per_point_lr shape. Expected {expected_shape}, got {per_point_lr.shape}")
-                    ppl = per_point_lr.float().contiguous()
-                    row_len = p.numel() // max(1, p.shape[0])
-                if not (p.is_contiguous() and grad.is_contiguous() and p.dtype == torch.float32):
+                st = self.state[p]
+                if not st:                                   # lazy state, same keys as the reference
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+                st["step"] += 1
+                t = st["step"]
+                # old-style bias correction folded into the step size, evaluated on the host in double
+                step_size = group["lr"] * ((1 - b2 ** t) ** 0.5 / (1 - b1 ** t))
+                mult, row_len = _validated_multiplier(p, group.get("per_point_lr"))
+                if not (p.is_contiguous() and g.is_contiguous() and p.dtype == torch.float32):
                     raise _lib.GsbError("PerPointAdam (B200) needs contiguous fp32 parameters and gradients")
-                entries.append(dict(param=p, grad=grad, exp_avg=state["exp_avg"], exp_avg_sq=state["exp_avg_sq"],
-                                    per_point_lr=ppl, step_size=step_size, beta1=beta1, beta2=beta2,
-                                    eps=group["eps"], weight_decay=group["weight_decay"], row_len=row_len))
-        if entries:
-            dev = entries[0]["param"].device
+                work.append(dict(param=p, grad=g, exp_avg=st["exp_avg"], exp_avg_sq=st["exp_avg_sq"], per_point_lr=mult,
+                                 step_size=step_size, beta1=b1, beta2=b2, eps=group["eps"],
+                                 weight_decay=group["weight_decay"], row_len=row_len))
+        if work:
+            dev = work[0]["param"].device
             if self._flags is None or self._flags.device != dev:
                 self._flags = torch.zeros(ADAM_MAX_TENSORS, dtype=torch.int32, device=dev)
-            launch_adam(entries, self._flags)
+            launch_adam(work, self._flags)
         return loss

@@ -137,6 +137,24 @@ def main():
     for k in P64:
         rec["g_" + k] = P64[k].grad.numpy()
     np.savez_compressed(os.path.join(OUT, "raster_tiny.npz"), **rec)
+    # ---- scene file formats (row f3): files written by instantsplat_b200.scene_io, parsed by the REFERENCE's
+    # own COLMAP text readers (/root/reference/scene/colmap_loader.py:159-182,248-275)
+    import tempfile
+    from instantsplat_b200 import scene_io
+    from instantsplat_b200.scenes import surface_scene
+    cl = _load("ref_colmap_loader", "scene/colmap_loader.py")
+    sc3 = surface_scene(300, 3, 64, 48, seed=21)
+    with tempfile.TemporaryDirectory() as td:
+        folder = scene_io.write_synthetic_source(td, sc3)
+        cams = cl.read_intrinsics_text(os.path.join(folder, "cameras.txt"))
+        imgs = cl.read_extrinsics_text(os.path.join(folder, "images.txt"))
+    ids = sorted(imgs)
+    np.savez(os.path.join(OUT, "scene_io.npz"),
+             cam_ids=np.array(sorted(cams)), cam_wh=np.array([[cams[i].width, cams[i].height] for i in sorted(cams)]),
+             cam_params=np.stack([cams[i].params for i in sorted(cams)]),
+             img_ids=np.array(ids), qvec=np.stack([imgs[i].qvec for i in ids]), tvec=np.stack([imgs[i].tvec for i in ids]),
+             img_cam=np.array([imgs[i].camera_id for i in ids]), names=np.array([imgs[i].name for i in ids]),
+             rot=np.stack([cl.qvec2rotmat(imgs[i].qvec) for i in ids]))
     print("wrote", sorted(os.listdir(OUT)))
 
 

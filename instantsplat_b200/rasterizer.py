@@ -98,7 +98,8 @@ def _forward(settings, means3D, scales, rotations, opacities, sh_dc, sh_rest, sh
     torch.cuda.current_stream().synchronize()          # the one host sync: R sizes the binning buffers
     R = int(host_r.item()) & 0xFFFFFFFF
     st.R = R
-    bin_bytes = L.gsb_binning_bytes(R, W, H)
+    # round the R-dependent request up to 32 MiB so the caching allocator can reuse the block of the previous call
+    bin_bytes = (L.gsb_binning_bytes(R, W, H) + (1 << 25) - 1) >> 25 << 25
     st.binning = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
     st.image = torch.empty(L.gsb_image_bytes(W, H), dtype=torch.uint8, device=dev)
     color = torch.empty(3, H, W, dtype=torch.float32, device=dev)

@@ -597,3 +597,46 @@ def test_knn_distcuda2_matches_bruteforce():
         ref = (d * d).topk(4, dim=1, largest=False).values[:, 1:].mean(dim=1).float()
         got = distCUDA2(pts.to(DEV)).cpu()
         assert torch.allclose(got, ref, rtol=1e-4, atol=1e-7), float((got - ref).abs().max())
+
+
+def test_per_point_adam_state_surgery_prune_and_cat():
+    """Row f4: the reference's densify/prune code edits `optimizer.state[p]` and `param_groups[i]["params"]` in place
+    (/root/reference/scene/gaussian_model.py:328-398: _prune_optimizer, cat_tensors_to_optimizer).  The drop-in keeps the
+    same state layout, so the same surgery works and later steps match the oracle on the resized tensors."""
+    import instantsplat_b200 as I
+    g = torch.Generator().manual_seed(5)
+    p0 = torch.randn(500, 3, generator=g)
+    param = torch.nn.Parameter(p0.to(DEV).clone())
+    opt = I.PerPointAdam([{"params": [param], "lr": 1e-2, "name": "xyz"}], lr=0.0, eps=1e-15)
+    ref_p, ref_m, ref_v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    g1 = torch.randn(500, 3, generator=g) * 1e-2
+    param.grad = g1.to(DEV)
+    opt.step()
+    O.per_point_adam_step(ref_p, g1, ref_m, ref_v, 1, 1e-2)
+    # ---- prune (reference _prune_optimizer)
+    mask = torch.rand(500, generator=g) > 0.3
+    group = opt.param_groups[0]
+    st = opt.state.get(group["params"][0])
+    st["exp_avg"] = st["exp_avg"][mask.to(DEV)]
+    st["exp_avg_sq"] = st["exp_avg_sq"][mask.to(DEV)]
+    del opt.state[group["params"][0]]
+    group["params"][0] = torch.nn.Parameter(group["params"][0][mask.to(DEV)].detach().clone().requires_grad_(True))
+    opt.state[group["params"][0]] = st
+    ref_p, ref_m, ref_v = ref_p[mask].clone(), ref_m[mask].clone(), ref_v[mask].clone()
+    # ---- cat new points (reference cat_tensors_to_optimizer)
+    ext = torch.randn(77, 3, generator=g)
+    st = opt.state.get(group["params"][0])
+    st["exp_avg"] = torch.cat((st["exp_avg"], torch.zeros(77, 3, device=DEV)), dim=0)
+    st["exp_avg_sq"] = torch.cat((st["exp_avg_sq"], torch.zeros(77, 3, device=DEV)), dim=0)
+    del opt.state[group["params"][0]]
+    group["params"][0] = torch.nn.Parameter(torch.cat((group["params"][0].detach(), ext.to(DEV)), dim=0).requires_grad_(True))
+    opt.state[group["params"][0]] = st
+    ref_p = torch.cat((ref_p, ext)); ref_m = torch.cat((ref_m, torch.zeros(77, 3))); ref_v = torch.cat((ref_v, torch.zeros(77, 3)))
+    newp = group["params"][0]
+    for it in (2, 3):
+        gi = torch.randn(newp.shape, generator=g) * 1e-2
+        newp.grad = gi.to(DEV)
+        opt.step()
+        O.per_point_adam_step(ref_p, gi, ref_m, ref_v, it, 1e-2)
+    np.testing.assert_allclose(newp.detach().cpu().numpy(), ref_p.numpy(), rtol=3e-6, atol=1e-7)
+    assert opt.state[newp]["step"] == 3 and opt.state[newp]["exp_avg"].shape == newp.shape

@@ -640,3 +640,41 @@ def test_per_point_adam_state_surgery_prune_and_cat():
         O.per_point_adam_step(ref_p, gi, ref_m, ref_v, it, 1e-2)
     np.testing.assert_allclose(newp.detach().cpu().numpy(), ref_p.numpy(), rtol=3e-6, atol=1e-7)
     assert opt.state[newp]["step"] == 3 and opt.state[newp]["exp_avg"].shape == newp.shape
+
+
+def test_dgr_C_surface_matches_module_path():
+    """shims/diff_gaussian_rasterization/_C: the upstream `_C.rasterize_gaussians(_backward)` / `mark_visible`
+    signatures give the same image and gradients as the GaussianRasterizer module."""
+    import sys
+    import instantsplat_b200 as I
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "shims"))
+    import diff_gaussian_rasterization as dgr
+    sc = random_scene(2500, 120, 88, seed=19)
+    rs = settings_for(sc, 3, torch.tensor([0.2, 0.1, 0.0]))
+    dev_p = {k: v.to(DEV) for k, v in sc.params.items()}
+    means = dev_p["xyz"].clone().requires_grad_(True)
+    scales = torch.exp(dev_p["scaling"]).requires_grad_(True)
+    rots = dev_p["rotation"].clone().requires_grad_(True)
+    opac = torch.sigmoid(dev_p["opacity"]).requires_grad_(True)
+    shs = torch.cat([dev_p["f_dc"], dev_p["f_rest"]], 1).requires_grad_(True)
+    m2d = torch.zeros(sc.P, 3, device=DEV, requires_grad=True)
+    img, radii = dgr.GaussianRasterizer(rs)(means3D=means, means2D=m2d, opacities=opac, shs=shs, scales=scales,
+                                             rotations=rots)
+    w = torch.rand(3, sc.height, sc.width, device=DEV)
+    (img * w).sum().backward()
+    e = torch.empty(0, device=DEV)
+    nr, color, radii2, geom, binning, imgbuf = dgr._C.rasterize_gaussians(
+        rs.bg, means.detach(), e, opac.detach(), scales.detach(), rots.detach(), 1.0, e, rs.viewmatrix, rs.projmatrix,
+        rs.tanfovx, rs.tanfovy, sc.height, sc.width, shs.detach(), 3, rs.campos, False, False)
+    assert nr > 0 and torch.equal(color, img.detach()) and torch.equal(radii2, radii)
+    assert geom.dtype == torch.uint8 and binning.dtype == torch.uint8
+    grads = dgr._C.rasterize_gaussians_backward(
+        rs.bg, means.detach(), radii2, e, scales.detach(), rots.detach(), 1.0, e, rs.viewmatrix, rs.projmatrix, rs.tanfovx,
+        rs.tanfovy, w, shs.detach(), 3, rs.campos, geom, nr, binning, imgbuf, False)
+    d_m2d, d_col, d_op, d_m3d, d_cov, d_sh, d_sc, d_rot = grads
+    assert d_col.numel() == 0 and d_cov.numel() == 0 and d_op.shape == (sc.P, 1)
+    for a, b in ((d_m2d, m2d.grad), (d_op, opac.grad), (d_m3d, means.grad), (d_sh, shs.grad), (d_sc, scales.grad),
+                 (d_rot, rots.grad)):
+        assert rel_err(a, b) < 1e-4
+    vis = dgr._C.mark_visible(means.detach(), rs.viewmatrix, rs.projmatrix)
+    assert torch.equal(vis, means.detach()[:, 2] > 0.2)

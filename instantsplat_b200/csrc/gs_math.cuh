@@ -316,6 +316,14 @@ GS_HD void project_color(const CamConst& c, const float* sh_dc, const float* sh_
 // centres can therefore be skipped when min q over it exceeds qthr (with a safety margin, so
 // pairs near the threshold are always evaluated by the exact per-pair rule).
 // ------------------------------------------------------------------------------------------
+GS_HD float gs_fdiv(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+
 GS_HD float cull_threshold(float opacity) {
   // returns < 0 when the Gaussian can never reach alpha >= 1/255
   if (!(opacity * 255.0f >= 0.999f)) return -1.0f;
@@ -330,15 +338,18 @@ GS_HD bool rect_may_contribute(float x, float y, float A, float B, float C, floa
   bool inx = (dx0 <= 0.f) && (dx1 >= 0.f);
   bool iny = (dy0 <= 0.f) && (dy1 >= 0.f);
   if (inx && iny) return true;
+  // The 1-D minimiser along an edge only has to be approximately right: q evaluated at any point of the
+  // edge is >= the true minimum, an error delta in the minimiser costs C*delta^2 (~1e-12 relative), far inside
+  // the safety margin of cull_threshold().  So the fast (MUFU.RCP based) division is enough on the device.
   float qmin = 3.0e38f;
   if (!inx) {
     float ex = dx0 > 0.f ? dx0 : dx1;
-    float dy = fminf(dy1, fmaxf(dy0, -B * ex / C));
+    float dy = fminf(dy1, fmaxf(dy0, gs_fdiv(-B * ex, C)));
     qmin = A * ex * ex + 2.f * B * ex * dy + C * dy * dy;
   }
   if (!iny) {
     float ey = dy0 > 0.f ? dy0 : dy1;
-    float dx = fminf(dx1, fmaxf(dx0, -B * ey / A));
+    float dx = fminf(dx1, fmaxf(dx0, gs_fdiv(-B * ey, A)));
     float q = A * dx * dx + 2.f * B * dx * ey + C * ey * ey;
     qmin = fminf(qmin, q);
   }

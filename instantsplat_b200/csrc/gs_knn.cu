@@ -142,13 +142,12 @@ k_knn3(int P, const float4* __restrict__ sorted, const Grid* gp, const unsigned 
     if (whole) break;
     if (b2 < FLT_MAX && bound > 0.f && b2 <= bound * bound) break;
   }
+  // fewer than 3 other points (P <= 3): the missing neighbours count as distance 0
   float sum = 0.f;
-  int cnt = 0;
-  if (b0 < FLT_MAX) { sum += b0; ++cnt; }
-  if (b1 < FLT_MAX) { sum += b1; ++cnt; }
-  if (b2 < FLT_MAX) { sum += b2; ++cnt; }
-  out[__float_as_uint(me.w)] = cnt ? sum / 3.0f : 0.f;
-  (void)cnt;
+  if (b0 < FLT_MAX) sum += b0;
+  if (b1 < FLT_MAX) sum += b1;
+  if (b2 < FLT_MAX) sum += b2;
+  out[__float_as_uint(me.w)] = sum / 3.0f;
 }
 
 int grid_dim(int P) {

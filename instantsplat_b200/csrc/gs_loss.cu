@@ -92,13 +92,6 @@ __device__ __forceinline__ void halo_store(const HaloRegs& h, float (*dst)[EWP])
     }
   }
 }
-__device__ __forceinline__ void stage_plane(float (*dst)[EWP], const float* __restrict__ src, int H, int W,
-                                            int x0, int y0) {
-  HaloRegs h;
-  halo_load(h, src, H, W, x0, y0);
-  halo_store(h, dst);
-}
-
 // Register-tiled separable 11-tap filter.  Horizontal: thread -> (row, 4 adjacent columns), inputs
 // fetched with four 128-bit shared loads.  Vertical: thread -> (column, 2 adjacent rows).
 // img planes [BC][H][W].  maps (optional) [3][BC][H][W].  sums[0] += sum|a-b| (if do_l1), sums[1] += sum ssim.

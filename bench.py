@@ -408,7 +408,26 @@ def run_b200(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(dom)
-    roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+    # pair statistics (instrumented re-run of the blend kernels, outside the timed region): the blend kernels are
+    # bound by instruction issue over (pixel, Gaussian) pairs, so the pair rate is the roof that binds them
+    pair = None
+    try:
+        ps = tr.blend_stats(view_for_step(sc.n_views, world, rank, 0))
+        sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_clk * 1e6            # warp instructions / s (4 schedulers per SM)
+        pair = dict(ps)
+        for d, kname in (("fwd", "blend_fwd"), ("bwd", "blend_bwd")):
+            if kname in kernels:
+                t = kernels[kname]["ms"] * 1e-3
+                pair[f"{d}_pairs_per_s"] = ps[f"{d}_pairs_evaluated"] / t
+                pair[f"{d}_warp_inst_per_64_pairs_at_full_issue"] = issue_peak * t / max(1, ps[f"{d}_warp_iters"])
+        pair["issue_peak_warp_inst_per_s"] = issue_peak
+        pair["note"] = ("pairs_evaluated = 64 x warp iterations (two 8x4 pixel blocks x one Gaussian); "
+                        "warp_inst_per_64_pairs_at_full_issue = the instruction budget per iteration if every issue "
+                        "slot were used: compare with the kernel's SASS count per iteration")
+    except Exception as e:
+        pair = {"error": f"{type(e).__name__}: {e}"}
+    roof = {"bound": "hbm", "kernel": dom, "pairs": pair, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
             "frac": kernels[dom]["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
             "alg_bytes_per_launch": kernels[dom]["alg_bytes"], "ms_per_launch": kernels[dom]["ms"],
             "note": "algorithmic bytes = SURVEY.md 8(d) formulas with the measured R; the blend kernels are "
@@ -444,7 +463,7 @@ def run_b200(args):
                 "h2d_bytes_per_step": int(stage.numel() * 4), "d2h_bytes_per_step": 8,
                 "api": "JointTrainer.step(view, gt=<pinned host image, H2D on a copy stream, double buffered>) + "
                        "loss_value() D2H every step"},
-        "gpu_launches": launches, "gpu_launches_note": "libgsb200.so kernels only (cub sort/scan launches excluded)",
+        "gpu_launches": launches, "gpu_launches_note": "every kernel on the path is libgsb200.so's own (no library sort/scan)",
         "dropin_boundary": dropin, "ref_python_pieces_gpu": torch_pieces, "kernels": kernels, "roofline": roof, "clocks": clocks, "cpu_baseline": cpu_base, "impl": "b200",
     }
     if world > 1:

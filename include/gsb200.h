@@ -104,18 +104,28 @@ GSB_API size_t gsb_geom_bytes(int32_t P);
 GSB_API size_t gsb_binning_bytes(int64_t R, int32_t width, int32_t height);
 GSB_API size_t gsb_image_bytes(int32_t width, int32_t height);
 
-/* Phase 1: per-Gaussian projection (+ fused pose / activations / SH->RGB), depth sort and tile
- * counting.  Writes radii [P] (int32) and the number of (Gaussian, tile) instances R to
- * *num_rendered_host (pinned host memory, valid after the stream reaches this point). */
+/* Forward, phase 1: per-Gaussian projection (+ fused pose / activations / SH->RGB), lossless tile culling,
+ * instance counts per Gaussian and per tile, tile-segment offsets.  Writes radii [P] (int32).  The number of
+ * (Gaussian, tile) instances R stays on the device; if status_host != NULL (pinned host memory, 4 words) the
+ * status words {R, 0, longest tile list, 0} are copied there asynchronously (valid once the stream reaches
+ * this point) -- a caller that wants an exactly-sized binning buffer waits for it, nobody else has to. */
 GSB_API int gsb_preprocess(const GsbCamera* cam, const GsbGaussians* g, void* geom, size_t geom_bytes,
-                   int32_t* radii, uint32_t* num_rendered_host, gsb_stream_t stream);
+                   int32_t* radii, uint32_t* status_host, gsb_stream_t stream);
 
-/* Phase 2: binning (duplicate, tile sort, ranges, slab gather) and the per-tile blend.
- * R must be the value produced by gsb_preprocess.  out_color [3,H,W]. */
+/* Forward, phase 2: binning (scatter into per-tile segments, per-tile depth sort in shared memory, slab
+ * gather) and the per-tile blend.  R is the instance CAPACITY the binning buffer was sized for
+ * (gsb_binning_bytes(R, w, h) <= binning_bytes); it need not be the exact count.  If the true count exceeds
+ * it the tile lists are truncated (memory-safe, image approximate) and status word 1 (overflow) is set.
+ * status_host (optional, pinned, 4 words): {R true, overflow, longest list, tiles sorted by the slow global
+ * path}, copied asynchronously after the blend has been enqueued.  out_color [3,H,W]. */
 GSB_API int gsb_render(const GsbCamera* cam, int32_t P, void* geom, void* binning, size_t binning_bytes,
-               int64_t R, void* image, float* out_color, gsb_stream_t stream);
+               int64_t R, void* image, float* out_color, uint32_t* status_host, gsb_stream_t stream);
 
-/* Backward of gsb_preprocess + gsb_render.  dL_dout [3,H,W]. */
+/* Device address of the 8 status words inside `geom` ([0] R, [1] overflow, [2] longest list, [3] slow-path
+ * tiles): lets device code (e.g. gsb_adam_step's skip flag) react to an overflow without a host round trip. */
+GSB_API uint32_t* gsb_status_device(void* geom, int32_t P);
+
+/* Backward of gsb_preprocess + gsb_render (same R as given to gsb_render).  dL_dout [3,H,W]. */
 GSB_API int gsb_backward(const GsbCamera* cam, const GsbGaussians* g, void* geom, void* binning, int64_t R,
                  void* image, const float* dL_dout, const GsbGrads* grads, gsb_stream_t stream);
 
@@ -155,6 +165,11 @@ typedef struct GsbAdamTensor {
 } GsbAdamTensor;
 /* flags: [n] uint32 scratch (device); gate g.norm()>0 per tensor is evaluated on the device. */
 GSB_API int gsb_adam_step(int32_t n, const GsbAdamTensor* tensors_host, uint32_t* flags, gsb_stream_t stream);
+/* Same, but the whole update is skipped on the device when *skip_if_nonzero != 0 (device pointer, may be NULL):
+ * pass gsb_status_device(geom, P) + 1 so that a binning overflow leaves the parameters untouched and the
+ * caller can redo the iteration with a larger buffer once it notices -- no host sync on the normal path. */
+GSB_API int gsb_adam_step_gated(int32_t n, const GsbAdamTensor* tensors_host, uint32_t* flags,
+                                const uint32_t* skip_if_nonzero, gsb_stream_t stream);
 
 /* flags[k] = (tensor k's scaled gradient has a non-zero element); the gate half of gsb_adam_step, exposed so
  * the multi-GPU path can all-reduce the flags before the fused exchange kernel. */
@@ -178,12 +193,15 @@ typedef struct GsbShardPiece { /* (one tensor's segment) intersected with (this 
   double step_size, beta1, beta2, eps;
 } GsbShardPiece;
 
-/* peer_grads / peer_params: host arrays of `world` device pointers to every rank's flat gradient / parameter
+/* skip_if_nonzero (device, may be NULL): when the word is non-zero the kernel returns without touching anything
+ * (the sum over ranks of the forward's overflow words, so every replica takes the same decision).
+ * peer_grads / peer_params: host arrays of `world` device pointers to every rank's flat gradient / parameter
  * buffer (own rank included).  exp_avg / exp_avg_sq: this rank's shard only, indexed by (element - shard_begin). */
 GSB_API int gsb_fused_rs_adam_ag(int32_t world, int32_t rank, const float* const* peer_grads,
                                  float* const* peer_params, float* exp_avg_shard, float* exp_avg_sq_shard,
                                  int64_t shard_begin, int32_t n_pieces, const GsbShardPiece* pieces,
-                                 const uint32_t* flags, float grad_scale, gsb_stream_t stream);
+                                 const uint32_t* flags, const uint32_t* skip_if_nonzero, float grad_scale,
+                                 gsb_stream_t stream);
 
 /* simple_knn._C.distCUDA2 (scene/gaussian_model.py:20,156-160; init only):
  * out[i] = mean squared distance from point i to its 3 nearest neighbours (exact).  points [P,3], out [P]. */
@@ -192,18 +210,24 @@ GSB_API int gsb_knn_mean_dist2(int32_t P, const float* points, float* out, void*
                                gsb_stream_t stream);
 
 /* Optional instrumentation (bench.py): per-kernel CUDA-event timing on the launching stream and a
- * count of this library's own kernel launches (cub launches are not counted). */
+ * count of this library's kernel launches (every launch on the path is the library's own). */
 enum {
-  GSB_K_PREPROCESS = 0, GSB_K_SORT_DEPTH, GSB_K_SCAN, GSB_K_DUPLICATE, GSB_K_SORT_TILE, GSB_K_GATHER,
+  GSB_K_PREPROCESS = 0, GSB_K_SORT_DEPTH /* unused since ABI 2 */, GSB_K_SCAN /* tile scan */,
+  GSB_K_DUPLICATE /* scatter */, GSB_K_SORT_TILE /* per-tile sort + slab gather */, GSB_K_GATHER /* unused */,
   GSB_K_BLEND_FWD, GSB_K_BLEND_BWD, GSB_K_PREPROCESS_BWD, GSB_K_LOSS_FWD, GSB_K_LOSS_BWD, GSB_K_ADAM,
   GSB_K_COUNT
 };
+/* Pair statistics of the blend kernels on the buffers of the last forward (and backward if dL_dout != NULL):
+ * stats (device, 8 x uint64) = {fwd warp iterations (64 evaluated pixel-Gaussian pairs each), fwd contributing
+ * pairs, bwd warp iterations, bwd contributing pairs, bwd warp iterations that reached the reduction, 0, 0, 0}. */
+GSB_API int gsb_blend_stats(const GsbCamera* cam, int32_t P, void* geom, void* binning, int64_t R, void* image,
+                            float* out_color, const float* dL_dout, unsigned long long* stats, gsb_stream_t stream);
 GSB_API void gsb_profile_enable(int on);
 GSB_API int gsb_profile_collect(double* ms_sum, int64_t* count, int n_ids);
 GSB_API uint64_t gsb_launch_count(void);
-/* Tuning switches: "blend_version" = 1 (one pixel per lane) | 2 (two pixels per lane, packed f32x2; default) | 3 (four
- * pixels per lane, 2 warps per tile; slower, experiment);
- * "stage_bulk" = 1 (slab chunks staged with cp.async.bulk/TMA + mbarrier, double buffered; default) | 0. */
+/* Tuning switches: "blend_version" = 1 (one pixel per lane, 8 warps per tile; the in-library cross-check) | 2 (two
+ * pixels per lane, packed f32x2; default); "stage_bulk" = 1 (slab chunks staged with cp.async.bulk/TMA +
+ * mbarrier, double buffered; default) | 0. */
 GSB_API int gsb_set_option(const char* name, int value);
 
 GSB_API const char* gsb_last_error(void);

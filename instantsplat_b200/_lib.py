@@ -63,7 +63,7 @@ EXPORTS = ("gsb_geom_bytes", "gsb_binning_bytes", "gsb_image_bytes", "gsb_prepro
            "gsb_loss_forward", "gsb_loss_backward", "gsb_adam_step", "gsb_last_error",
            "gsb_abi_version", "gsb_profile_enable", "gsb_profile_collect", "gsb_launch_count", "gsb_set_option", "gsb_adam_gate",
            "gsb_ipc_alloc", "gsb_ipc_open", "gsb_ipc_close", "gsb_ipc_free", "gsb_fused_rs_adam_ag",
-           "gsb_knn_scratch_bytes", "gsb_knn_mean_dist2")
+           "gsb_knn_scratch_bytes", "gsb_knn_mean_dist2", "gsb_status_device", "gsb_adam_step_gated", "gsb_blend_stats")
 KERNEL_IDS = ("preprocess", "sort_depth", "scan", "duplicate", "sort_tile", "gather", "blend_fwd", "blend_bwd",
               "preprocess_bwd", "loss_fwd", "loss_bwd", "adam")
 
@@ -100,7 +100,13 @@ def lib() -> ctypes.CDLL:
     L.gsb_image_bytes.restype = sz
     L.gsb_image_bytes.argtypes = [i32, i32]
     L.gsb_preprocess.argtypes = [ctypes.POINTER(GsbCamera), ctypes.POINTER(GsbGaussians), vp, sz, vp, vp, vp]
-    L.gsb_render.argtypes = [ctypes.POINTER(GsbCamera), i32, vp, vp, sz, i64, vp, vp, vp]
+    L.gsb_render.argtypes = [ctypes.POINTER(GsbCamera), i32, vp, vp, sz, i64, vp, vp, vp, vp]
+    L.gsb_blend_stats.argtypes = [ctypes.POINTER(GsbCamera), i32, vp, vp, i64, vp, vp, vp, vp, vp]
+    L.gsb_blend_stats.restype = ctypes.c_int
+    L.gsb_status_device.argtypes = [vp, i32]
+    L.gsb_status_device.restype = vp
+    L.gsb_adam_step_gated.argtypes = [i32, ctypes.POINTER(GsbAdamTensor), vp, vp, vp]
+    L.gsb_adam_step_gated.restype = ctypes.c_int
     L.gsb_backward.argtypes = [ctypes.POINTER(GsbCamera), ctypes.POINTER(GsbGaussians), vp, vp, i64, vp, vp,
                                ctypes.POINTER(GsbGrads), vp]
     L.gsb_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
@@ -124,7 +130,7 @@ def lib() -> ctypes.CDLL:
     L.gsb_ipc_close.argtypes = [vp]
     L.gsb_ipc_free.argtypes = [vp]
     L.gsb_fused_rs_adam_ag.argtypes = [i32, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp, i64, i32,
-                                       ctypes.POINTER(GsbShardPiece), vp, ctypes.c_float, vp]
+                                       ctypes.POINTER(GsbShardPiece), vp, vp, ctypes.c_float, vp]
     L.gsb_knn_scratch_bytes.argtypes = [i32]
     L.gsb_knn_scratch_bytes.restype = sz
     L.gsb_knn_mean_dist2.argtypes = [i32, vp, vp, vp, sz, vp]

@@ -89,7 +89,9 @@ __device__ __forceinline__ void adam_elem(const AdamT& t, bool gate, float lr_mu
   p = __fadd_rn(p, __fmul_rn(-(t.step * lr_mul), upd));
 }
 
-__global__ void __launch_bounds__(kAT) k_adam(AdamArgs a, const unsigned int* __restrict__ flags) {
+__global__ void __launch_bounds__(kAT) k_adam(AdamArgs a, const unsigned int* __restrict__ flags,
+                                              const unsigned int* __restrict__ skip) {
+  if (skip && *skip) return;     // e.g. the forward's overflow word: the caller redoes the step with larger buffers
   const int k = find_tensor(a, blockIdx.x);
   const AdamT& t = a.t[k];
   const bool gate = flags[k] != 0;
@@ -183,7 +185,8 @@ extern "C" GSB_API int gsb_adam_gate(int32_t n, const GsbAdamTensor* ts, uint32_
   return finish(e, "gsb_adam_gate");
 }
 
-extern "C" GSB_API int gsb_adam_step(int32_t n, const GsbAdamTensor* ts, uint32_t* flags, gsb_stream_t stream_) {
+extern "C" GSB_API int gsb_adam_step_gated(int32_t n, const GsbAdamTensor* ts, uint32_t* flags,
+                                           const uint32_t* skip_if_nonzero, gsb_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (n < 0 || n > GSB_ADAM_MAX_TENSORS || (n > 0 && (!ts || !flags))) {
     gsb_set_error("gsb_adam_step: bad argument");
@@ -199,9 +202,13 @@ extern "C" GSB_API int gsb_adam_step(int32_t n, const GsbAdamTensor* ts, uint32_
     gsb_count_launch(2);
     int slot = gsb_prof_begin(GSB_K_ADAM, st);
     k_adam_gate<<<n * kGateSlots, kAT, 0, st>>>(a, flags);
-    k_adam<<<nb, kAT, 0, st>>>(a, flags);
+    k_adam<<<nb, kAT, 0, st>>>(a, flags, skip_if_nonzero);
     gsb_prof_end(slot, st);
     e = cudaGetLastError();
   }
   return finish(e, "gsb_adam_step");
+}
+
+extern "C" GSB_API int gsb_adam_step(int32_t n, const GsbAdamTensor* ts, uint32_t* flags, gsb_stream_t stream) {
+  return gsb_adam_step_gated(n, ts, flags, nullptr, stream);
 }

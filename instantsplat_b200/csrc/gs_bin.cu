@@ -1,0 +1,320 @@
+// Binning for the B200 rasterizer: from per-Gaussian splat records to per-tile, depth-ordered slabs --
+// hand-written, no library sort/scan, no host round trip.
+//
+// The reference pipeline (InclusiveSum -> duplicateWithKeys -> 64-bit SortPairs ->
+// identifyTileRanges, driven from /root/reference/gaussian_renderer/__init__.py:126-135) sorts ALL R
+// (tile | depth) keys globally and needs R on the host to size its buffers.  Here the order is produced
+// tile-locally instead:
+//
+//   k_preprocess   (gs_raster.cu) counts instances per tile with RED.ADD while it projects     -> tcount[T]
+//   k_tile_scan    one CTA: exclusive scan of the T (<= 65535) tile counts                      -> tstart[T], R
+//   k_scatter      one thread per Gaussian (any order): (depth bits << 32 | id) appended to its tiles' segments
+//                  through per-tile atomic cursors
+//   k_tile_sort    one CTA per tile: the segment is sorted by the unique 64-bit key in SHARED MEMORY
+//                  (one adaptive-range bucket pass + per-bucket insertion sort; flip-bitonic fallback for
+//                  skewed depth distributions), then the splat records are gathered into the tile's contiguous
+//                  slab (3 x float4 per instance) that the blend kernels stage with TMA bulk copies
+//
+// Result order = (tile, depth bits ascending, Gaussian index ascending): exactly the reference's stable radix
+// sort of keys emitted in index order (Appendix A.2.9) -- deterministic although emission uses atomics.
+// Every kernel reads R / offsets from device memory; the host only supplies a capacity.  If the true R
+// exceeds it, lists are truncated memory-safely and status[kStOverflow] is raised for the caller to see.
+#include "gs_internal.cuh"
+#include "gs_tiles.cuh"
+
+using namespace gsb;
+
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ------------------------------------------------------------------------------------------
+// k_tile_scan
+// ------------------------------------------------------------------------------------------
+constexpr int kScanT = 1024;
+__global__ void __launch_bounds__(kScanT) k_tile_scan(GeomView gv, int ntiles) {
+  __shared__ unsigned long long s_warp[32];
+  __shared__ uint32_t s_max[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (ntiles + kScanT - 1) / kScanT;
+  const int lo = tid * per, hi = min(ntiles, lo + per);
+  unsigned long long sum = 0;
+  uint32_t mx = 0;
+  for (int t = lo; t < hi; ++t) { const uint32_t c = gv.tcount[t]; sum += c; mx = max(mx, c); }
+  unsigned long long inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  if (lane == 0) s_max[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = s_warp[lane];
+    uint32_t m = s_max[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+      m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    s_warp[lane] = w;
+    if (lane == 0) s_max[0] = m;
+  }
+  __syncthreads();
+  unsigned long long run = (inc - sum) + (warp ? s_warp[warp - 1] : 0ull);
+  for (int t = lo; t < hi; ++t) {
+    gv.tstart[t] = (uint32_t)min(run, 0xFFFFFFF0ull);     // saturating: such a tile is beyond any capacity
+    gv.tcursor[t] = 0u;
+    run += gv.tcount[t];
+  }
+  if (tid == kScanT - 1) {
+    gv.status[kStR] = (uint32_t)min(s_warp[31], 0xFFFFFFF0ull);
+    gv.status[kStOverflow] = 0u;
+    gv.status[kStMaxList] = s_max[0];
+    gv.status[kStHugeTiles] = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_scatter: one thread per Gaussian
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_scatter(int P, GeomView gv, BinView bv, int W, int H, int gx, int exact_cull, uint32_t cap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = i < P ? gv.tiles[i] : 0u;
+  SplatRect p;
+  p.x = p.y = p.A = p.B = p.C = 0.f; p.qthr = -1.f;
+  p.rx0 = p.rx1 = p.ry0 = p.ry1 = 0;
+  unsigned long long key = 0ull;
+  bool coop = false;
+  TileSink sink{gv.tcount, gv.tstart, gv.tcursor, bv.pairs, cap};
+  if (n) {
+    const float4 a = gv.xyAB[i], b = gv.Codq[i];
+    const uint2 rc = gv.rect[i];
+    p.x = a.x; p.y = a.y; p.A = a.z; p.B = a.w; p.C = b.x; p.qthr = b.w;
+    p.rx0 = rc.x & 0xFFFF; p.rx1 = rc.x >> 16; p.ry0 = rc.y & 0xFFFF; p.ry1 = rc.y >> 16;
+    key = ((unsigned long long)__float_as_uint(b.z) << 32) | (unsigned long long)(uint32_t)i;
+    coop = (p.rx1 - p.rx0) * (p.ry1 - p.ry0) > kCoopTiles;
+    if (!coop) visit_tiles(p, W, H, gx, exact_cull != 0, sink, key);
+  }
+  visit_tiles_coop(coop, p, W, H, gx, exact_cull != 0, sink, key);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_tile_sort
+// ------------------------------------------------------------------------------------------
+// Compare-exchange network that sorts a[0..n) ascending for ANY n: the "flip" formulation of bitonic sort
+// (first step of every merge pairs i with its mirror image, all exchanges ascending), so indices >= n act as
+// +infinity and are simply skipped.  `a` may be shared or global memory (one CTA owns it).
+template <int NT>
+__device__ __forceinline__ void cta_bitonic(unsigned long long* a, uint32_t n) {
+  uint32_t N = 1;
+  while (N < n) N <<= 1;
+  for (uint32_t k = 2; k <= N; k <<= 1) {
+    for (uint32_t t = threadIdx.x; t < N / 2; t += NT) {          // flip step
+      const uint32_t half = k >> 1, blk = t / half, off = t - blk * half;
+      const uint32_t i = blk * k + off, p = blk * k + (k - 1 - off);
+      if (p < n) {
+        const unsigned long long x = a[i], y = a[p];
+        if (x > y) { a[i] = y; a[p] = x; }
+      }
+    }
+    __syncthreads();
+    for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+      for (uint32_t t = threadIdx.x; t < N / 2; t += NT) {
+        const uint32_t i = 2 * j * (t / j) + (t % j), p = i + j;
+        if (p < n) {
+          const unsigned long long x = a[i], y = a[p];
+          if (x > y) { a[i] = y; a[p] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ void gather_slab(const GeomView& gv, const BinView& bv, const unsigned long long* sorted,
+                                            uint32_t start, uint32_t n, int nthreads) {
+  for (uint32_t j = threadIdx.x; j < n; j += nthreads) {
+    const uint32_t i = (uint32_t)sorted[j];
+    const float4 a = gv.xyAB[i], b = gv.Codq[i], c = gv.rgbr[i];
+    const size_t e = (size_t)start + j;
+    // conic pre-scaled into the log2 domain: power*log2(e) = A' dx^2 + B' dx dy + C' dy^2
+    bv.s0[e] = make_float4(a.x, a.y, -0.5f * kLog2e * a.z, -kLog2e * a.w);
+    bv.s1[e] = make_float4(-0.5f * kLog2e * b.x, b.y, 0.5f * kLog2e * b.w, __uint_as_float(i));
+    bv.s2[e] = make_float4(c.x, c.y, c.z, 0.f);
+  }
+}
+
+constexpr uint32_t kSkew = 24;     // a bucket longer than this sends the tile to the bitonic fallback
+
+// NT threads, KPT keys per thread: handles lists of n_lo <= n <= n_hi <= NT*KPT entries (other tiles return at
+// once, so several size classes can be launched over the same grid).  HUGE: any n, sorted in global memory.
+template <int NT, int KPT, bool HUGE>
+__global__ void __launch_bounds__(NT)
+k_tile_sort(GeomView gv, BinView bv, uint32_t cap, uint32_t n_lo, uint32_t n_hi) {
+  constexpr int CAP = NT * KPT;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  unsigned long long* sorted = reinterpret_cast<unsigned long long*>(smraw);   // [CAP]
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smraw + (size_t)CAP * 8);       // [CAP] buckets
+  __shared__ uint32_t s_w[32], s_w2[32];
+  __shared__ unsigned long long s_mul;
+  __shared__ uint32_t s_dmin;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t start = gv.tstart[tile], cnt = gv.tcount[tile], cur = gv.tcursor[tile];
+  const uint32_t avail = start < cap ? cap - start : 0u;
+  const uint32_t n = min(min(cnt, cur), avail);
+  if (n < n_lo || n > n_hi) return;
+  if (tid == 0) {
+    const uint32_t s = min(start, cap);
+    bv.ranges[tile] = make_uint2(s, s + n);
+    if (cnt > avail) atomicOr(gv.status + kStOverflow, 1u);
+    if (HUGE) atomicAdd(gv.status + kStHugeTiles, 1u);
+  }
+  if (n == 0) return;
+  if (HUGE) {
+    unsigned long long* seg = bv.pairs + start;
+    cta_bitonic<NT>(seg, n);
+    gather_slab(gv, bv, seg, start, n, NT);
+    return;
+  }
+  // ---- load keys, depth range
+  unsigned long long k[KPT];
+  uint32_t dmin = 0xFFFFFFFFu, dmax = 0u;
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) {
+    const uint32_t idx = (uint32_t)(j * NT + tid);
+    k[j] = idx < n ? bv.pairs[(size_t)start + idx] : ~0ull;
+    if (idx < n) { const uint32_t d = (uint32_t)(k[j] >> 32); dmin = min(dmin, d); dmax = max(dmax, d); }
+    hist[idx] = 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  }
+  if (lane == 0) { s_w[warp] = dmin; s_w2[warp] = dmax; }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t a = lane < NT / 32 ? s_w[lane] : 0xFFFFFFFFu, b = lane < NT / 32 ? s_w2[lane] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if (lane == 0) {
+      s_dmin = a;
+      // bucket(d) = ((d - dmin) * mul) >> 32 is monotone in d and < CAP
+      s_mul = ((unsigned long long)CAP << 32) / ((unsigned long long)(b - a) + 1ull);
+    }
+  }
+  __syncthreads();
+  dmin = s_dmin;
+  const unsigned long long mul = s_mul;
+  uint32_t bkt[KPT];
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) {
+    const uint32_t idx = (uint32_t)(j * NT + tid);
+    bkt[j] = 0u;
+    if (idx < n) {
+      bkt[j] = (uint32_t)(((unsigned long long)((uint32_t)(k[j] >> 32) - dmin) * mul) >> 32);
+      atomicAdd(hist + bkt[j], 1u);
+    }
+  }
+  __syncthreads();
+  // ---- exclusive scan of the CAP bucket counts (thread t owns buckets [t*KPT, (t+1)*KPT))
+  uint32_t c[KPT], sum = 0u, big = 0u;
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) { c[j] = hist[tid * KPT + j]; sum += c[j]; big = max(big, c[j]); }
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  const bool skew = __syncthreads_or(big > kSkew) != 0;
+  if (warp == 0) {
+    uint32_t w = lane < NT / 32 ? s_w[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    s_w[lane] = w;
+  }
+  __syncthreads();
+  uint32_t run = (inc - sum) + (warp ? s_w[warp - 1] : 0u);
+  const uint32_t my_begin = run;
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) { hist[tid * KPT + j] = run; run += c[j]; }
+  __syncthreads();
+  // ---- scatter into buckets (order inside a bucket is arbitrary here)
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) {
+    const uint32_t idx = (uint32_t)(j * NT + tid);
+    if (idx < n) sorted[atomicAdd(hist + bkt[j], 1u)] = k[j];
+  }
+  __syncthreads();
+  if (skew) {
+    cta_bitonic<NT>(sorted, n);
+  } else {
+    // ---- each thread finishes its own KPT consecutive buckets with an insertion sort on the full 64-bit key
+    uint32_t b0 = my_begin;
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+      const uint32_t b1 = b0 + c[j];
+      for (uint32_t a = b0 + 1; a < b1; ++a) {
+        const unsigned long long v = sorted[a];
+        uint32_t q = a;
+        while (q > b0 && sorted[q - 1] > v) { sorted[q] = sorted[q - 1]; --q; }
+        sorted[q] = v;
+      }
+      b0 = b1;
+    }
+    __syncthreads();
+  }
+  gather_slab(gv, bv, sorted, start, n, NT);
+}
+
+constexpr int kSmallNT = 256, kSmallKPT = 8;     // lists of up to 2048 entries: 24 KB shared memory
+constexpr int kLargeNT = 512, kLargeKPT = 16;    // up to 8192 entries: 96 KB shared memory
+constexpr uint32_t kSmallCap = kSmallNT * kSmallKPT, kLargeCap = kLargeNT * kLargeKPT;
+constexpr size_t kSmallSmem = (size_t)kSmallCap * 12, kLargeSmem = (size_t)kLargeCap * 12;
+
+}  // namespace
+
+int gsb_launch_tile_scan(const GeomView& gv, int ntiles, cudaStream_t st) {
+  ProfScope ps(GSB_K_SCAN, st);
+  k_tile_scan<<<1, kScanT, 0, st>>>(gv, ntiles);
+  return GSB_OK;
+}
+
+int gsb_launch_binning(int P, const GeomView& gv, const BinView& bv, int W, int H, int exact_cull, uint32_t cap,
+                       cudaStream_t st) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  GSB_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    GSB_CUDA(cudaFuncSetAttribute(k_tile_sort<kLargeNT, kLargeKPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kLargeSmem));
+    attr_set[dev] = true;
+  }
+  const int gx = (W + kBlock - 1) / kBlock, gy = (H + kBlock - 1) / kBlock;
+  if (P > 0) {
+    ProfScope ps(GSB_K_DUPLICATE, st);
+    k_scatter<<<(P + kThreads - 1) / kThreads, kThreads, 0, st>>>(P, gv, bv, W, H, gx, exact_cull, cap);
+  }
+  {
+    ProfScope ps(GSB_K_SORT_TILE, st, 3);
+    k_tile_sort<kSmallNT, kSmallKPT, false><<<gx * gy, kSmallNT, kSmallSmem, st>>>(gv, bv, cap, 0u, kSmallCap);
+    k_tile_sort<kLargeNT, kLargeKPT, false><<<gx * gy, kLargeNT, kLargeSmem, st>>>(gv, bv, cap, kSmallCap + 1, kLargeCap);
+    k_tile_sort<kLargeNT, 1, true><<<gx * gy, kLargeNT, 0, st>>>(gv, bv, cap, kLargeCap + 1, 0xFFFFFFFFu);
+  }
+  GSB_CUDA(cudaGetLastError());
+  return GSB_OK;
+}

@@ -1,0 +1,693 @@
+// Per-tile alpha blend of the B200 rasterizer, forward and backward (SURVEY.md Appendix A.2.10 / A.3;
+// reference call site /root/reference/gaussian_renderer/__init__.py:126-135).
+//
+//   k_blend_fwd2 / k_blend_bwd2   CTA = 16x16 tile (4 warps), warp = 8x8 block, TWO pixels per lane sharing dx;
+//                                 per-pair math issued as packed f32x2 (FFMA2/FMUL2/FADD2); slab chunks staged by
+//                                 TMA bulk copies (cp.async.bulk + mbarrier), double buffered; per-warp
+//                                 ballot-compacted exact sub-tile culling
+//   k_blend_fwd / k_blend_bwd     v1: one pixel per lane, 8 warps per tile, cooperative staging -- the first
+//                                 correct version, kept as the in-library cross-check (gsb_set_option)
+#include "gs_internal.cuh"
+
+using namespace gsb;
+
+namespace {
+
+constexpr float kLn2 = 0.6931471805599453f;
+
+#ifndef GSB_CHUNK
+#define GSB_CHUNK 256
+#endif
+#ifndef GSB_FWD_MINB
+#define GSB_FWD_MINB 7
+#endif
+#ifndef GSB_BWD_MINB
+#define GSB_BWD_MINB 6
+#endif
+constexpr int kChunk1 = 256;           // v1 blend kernels: one entry per thread
+constexpr int kChunk = GSB_CHUNK;      // slab entries staged per step in the blend kernels
+
+// ------------------------------------------------------------------------------------------
+// blend
+// ------------------------------------------------------------------------------------------
+struct PairEval { float dx, dy, power, G, alpha; };   // power is in the log2 domain (power * log2 e)
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ PairEval pair_eval(const float4& e0, const float4& e1, float fx, float fy) {
+  PairEval r;
+  r.dx = e0.x - fx;
+  r.dy = e0.y - fy;
+  r.power = e0.z * r.dx * r.dx + (e0.w * r.dx + e1.x * r.dy) * r.dy;
+  r.G = ex2_approx(r.power);   // MUFU.EX2 directly (valid pairs have power >= -8)
+  r.alpha = fminf(0.99f, e1.y * r.G);
+  return r;
+}
+
+// cull test on a slab entry: q' = -(A'dx^2 + B'dxdy + C'dy^2) = q * log2(e)/2 against qthr' = qthr * log2(e)/2
+__device__ __forceinline__ bool slab_may_contribute(const float4& e0, const float4& e1, float rx0, float ry0,
+                                                    float rx1, float ry1) {
+  return rect_may_contribute(e0.x, e0.y, -e0.z, -0.5f * e0.w, -e1.x, e1.z, rx0, ry0, rx1, ry1);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_blend_fwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
+            const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+            float* __restrict__ out_color, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+  __shared__ float4 sm0[kChunk1], sm1[kChunk1], sm2[kChunk1];
+  const int tile = blockIdx.x;
+  const int tx = tile % gx, ty = tile / gx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sx0 = tx * kBlock + (warp & 1) * 8, sy0 = ty * kBlock + (warp >> 1) * 4;
+  const int px = sx0 + (lane & 7), py = sy0 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const float fx = (float)px, fy = (float)py;
+  const float rx0 = (float)sx0, ry0 = (float)sy0;
+  const float rx1 = (float)min(sx0 + 7, W - 1), ry1 = (float)min(sy0 + 3, H - 1);
+  const uint2 rg = ranges[tile];
+  const int n = (int)(rg.y - rg.x);
+  float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f;
+  uint32_t last = 0;
+  bool done = !inside;
+  bool wdone = !(sx0 < W && sy0 < H);
+  for (int base = 0; base < n; base += kChunk1) {
+    const int cnt = min(kChunk1, n - base);
+    if ((int)threadIdx.x < cnt) {
+      size_t e = (size_t)rg.x + base + threadIdx.x;
+      sm0[threadIdx.x] = s0[e];
+      sm1[threadIdx.x] = s1[e];
+      sm2[threadIdx.x] = s2[e];
+    }
+    __syncthreads();
+    if (!wdone) {
+      for (int b = 0; b < cnt; b += 32) {
+        const int j = b + lane;
+        bool hit = false;
+        if (j < cnt) {
+          float4 e0 = sm0[j], e1 = sm1[j];
+          hit = slab_may_contribute(e0, e1, rx0, ry0, rx1, ry1);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+          const int k = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float4 e0 = sm0[b + k], e1 = sm1[b + k];
+          PairEval pe = pair_eval(e0, e1, fx, fy);
+          bool valid = !done && pe.power <= 0.f && pe.alpha >= kAlphaMin;
+          float testT = T * (1.f - pe.alpha);
+          if (valid && testT < kTEps) { done = true; valid = false; }
+          if (valid) {
+            const float4 c = sm2[b + k];
+            float w = pe.alpha * T;
+            Cr += c.x * w; Cg += c.y * w; Cb += c.z * w;
+            T = testT;
+            last = (uint32_t)(base + b + k + 1);
+          }
+        }
+        if (__all_sync(0xffffffffu, done)) { wdone = true; break; }
+      }
+    }
+    if (__syncthreads_and(wdone)) break;
+  }
+  if (inside) {
+    size_t pix = (size_t)py * W + px, hw = (size_t)W * H;
+    final_T[pix] = T;
+    n_contrib[pix] = last;
+    out_color[pix] = Cr + T * bg[0];
+    out_color[hw + pix] = Cg + T * bg[1];
+    out_color[2 * hw + pix] = Cb + T * bg[2];
+  }
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Reduce 9 per-lane values over the warp with 14 shuffles.  On return, lane l with (l & 3) == 0
+// holds the total of v[l >> 2] in v[0]; every lane holds the total of v[8] in v[8].
+__device__ __forceinline__ void warp_reduce9(float* v, int lane) {
+  const unsigned full = 0xffffffffu;
+  float b[4], c[2], d;
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float send = hi ? v[k] : v[k + 4];
+      float keep = hi ? v[k + 4] : v[k];
+      b[k] = keep + __shfl_xor_sync(full, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float send = hi ? b[k] : b[k + 2];
+      float keep = hi ? b[k + 2] : b[k];
+      c[k] = keep + __shfl_xor_sync(full, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+    float send = hi ? c[0] : c[1];
+    float keep = hi ? c[1] : c[0];
+    d = keep + __shfl_xor_sync(full, send, 4);
+  }
+  d += __shfl_xor_sync(full, d, 2);
+  d += __shfl_xor_sync(full, d, 1);
+  v[0] = d;
+  float e = v[8];
+  e += __shfl_xor_sync(full, e, 16);
+  e += __shfl_xor_sync(full, e, 8);
+  e += __shfl_xor_sync(full, e, 4);
+  e += __shfl_xor_sync(full, e, 2);
+  e += __shfl_xor_sync(full, e, 1);
+  v[8] = e;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_blend_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
+            const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+            const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
+            const float* __restrict__ dL_dpix, float* __restrict__ dacc) {
+  __shared__ float4 sm0[kChunk1], sm1[kChunk1], sm2[kChunk1];
+  __shared__ int s_bmax;
+  const int tile = blockIdx.x;
+  const int tx = tile % gx, ty = tile / gx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sx0 = tx * kBlock + (warp & 1) * 8, sy0 = ty * kBlock + (warp >> 1) * 4;
+  const int px = sx0 + (lane & 7), py = sy0 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const float fx = (float)px, fy = (float)py;
+  const float rx0 = (float)sx0, ry0 = (float)sy0;
+  const float rx1 = (float)min(sx0 + 7, W - 1), ry1 = (float)min(sy0 + 3, H - 1);
+  const uint2 rg = ranges[tile];
+  const size_t pix = (size_t)py * W + px, hw = (size_t)W * H;
+  const float T_final = inside ? final_T[pix] : 0.f;
+  const int last_contrib = inside ? (int)n_contrib[pix] : 0;
+  float dLr = 0.f, dLg = 0.f, dLb = 0.f;
+  if (inside) { dLr = dL_dpix[pix]; dLg = dL_dpix[hw + pix]; dLb = dL_dpix[2 * hw + pix]; }
+  const float bg_dot = bg[0] * dLr + bg[1] * dLg + bg[2] * dLb;
+  int wmax = last_contrib;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  if (threadIdx.x == 0) s_bmax = 0;
+  __syncthreads();
+  if (lane == 0) atomicMax(&s_bmax, wmax);
+  __syncthreads();
+  const int bmax = s_bmax;
+  float T = T_final;
+  float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, last_alpha = 0.f, last_r = 0.f, last_g = 0.f, last_b = 0.f;
+  const int nchunks = (bmax + kChunk1 - 1) / kChunk1;
+  for (int ch = nchunks - 1; ch >= 0; --ch) {
+    const int base = ch * kChunk1;
+    const int cnt = min(kChunk1, bmax - base);
+    if ((int)threadIdx.x < cnt) {
+      size_t e = (size_t)rg.x + base + threadIdx.x;
+      sm0[threadIdx.x] = s0[e];
+      sm1[threadIdx.x] = s1[e];
+      sm2[threadIdx.x] = s2[e];
+    }
+    __syncthreads();
+    if (base < wmax) {
+      for (int b = (cnt - 1) & ~31; b >= 0; b -= 32) {
+        if (base + b >= wmax) continue;
+        const int j = b + lane;
+        bool hit = false;
+        if (j < cnt && base + j < wmax) {
+          float4 e0 = sm0[j], e1 = sm1[j];
+          hit = slab_may_contribute(e0, e1, rx0, ry0, rx1, ry1);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+          const int k = 31 - __clz(mask);
+          mask &= ~(1u << k);
+          const int pos = base + b + k;
+          const float4 e0 = sm0[b + k], e1 = sm1[b + k];
+          PairEval pe = pair_eval(e0, e1, fx, fy);
+          const bool valid = inside && pos < last_contrib && pe.power <= 0.f && pe.alpha >= kAlphaMin;
+          if (!__any_sync(0xffffffffu, valid)) continue;
+          float v[9];
+#pragma unroll
+          for (int u = 0; u < 9; ++u) v[u] = 0.f;
+          if (valid) {
+            const float4 c = sm2[b + k];
+            const float inv1ma = rcp_approx(1.f - pe.alpha);      // 1-alpha in [0.01, 1]
+            T = T * inv1ma;
+            const float dchannel_dcolor = pe.alpha * T;
+            acc_r = last_alpha * last_r + (1.f - last_alpha) * acc_r; last_r = c.x;
+            acc_g = last_alpha * last_g + (1.f - last_alpha) * acc_g; last_g = c.y;
+            acc_b = last_alpha * last_b + (1.f - last_alpha) * acc_b; last_b = c.z;
+            float dL_dalpha = (c.x - acc_r) * dLr + (c.y - acc_g) * dLg + (c.z - acc_b) * dLb;
+            dL_dalpha *= T;
+            last_alpha = pe.alpha;
+            dL_dalpha -= T_final * inv1ma * bg_dot;
+            const float dL_dG = e1.y * dL_dalpha;
+            const float gdx = pe.G * pe.dx, gdy = pe.G * pe.dy;
+            // -A = 2 ln2 A', -B = ln2 B', -C = 2 ln2 C'
+            v[0] = dL_dG * kLn2 * (2.f * gdx * e0.z + gdy * e0.w);
+            v[1] = dL_dG * kLn2 * (2.f * gdy * e1.x + gdx * e0.w);
+            v[2] = -0.5f * gdx * pe.dx * dL_dG;
+            v[3] = -gdx * pe.dy * dL_dG;
+            v[4] = -0.5f * gdy * pe.dy * dL_dG;
+            v[5] = pe.G * dL_dalpha;
+            v[6] = dchannel_dcolor * dLr;
+            v[7] = dchannel_dcolor * dLg;
+            v[8] = dchannel_dcolor * dLb;
+          }
+          warp_reduce9(v, lane);
+          // lane 4i holds total i (i < 8): pull 4 consecutive totals into lanes 0 and 16 and issue two
+          // 128-bit reductions (REDG.E.ADD.F32x4) + one scalar instead of nine scalar atomics
+          const float a1 = __shfl_down_sync(0xffffffffu, v[0], 4);
+          const float a2 = __shfl_down_sync(0xffffffffu, v[0], 8);
+          const float a3 = __shfl_down_sync(0xffffffffu, v[0], 12);
+          float* dst = dacc + (size_t)__float_as_uint(e1.w) * 12;
+          if ((lane & 15) == 0) red_add_v4(dst + (lane >> 2), v[0], a1, a2, a3);
+          if (lane == 1) atomicAdd(dst + 8, v[8]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// blend v2: 4 warps per tile, each warp owns an 8x8 block = two 8x4 halves; every lane carries TWO
+// pixels (x, y) and (x, y+4) that share dx, and the per-pair arithmetic is issued as packed
+// FFMA2/FMUL2/FADD2 (Blackwell f32x2), so one instruction stream serves 64 (pixel, Gaussian) pairs.
+// The sub-tile cull is evaluated per half and the loop runs over the union of the two masks.
+// ------------------------------------------------------------------------------------------
+constexpr int kThreads2 = 128;
+
+// ------------------------------------------------------------------------------------------
+// TMA (bulk async copy) staging of the per-tile slabs: one elected thread arms an mbarrier with the
+// byte count and issues cp.async.bulk.shared.global for the three slab arrays of the NEXT chunk
+// while the CTA blends the current one (double buffered).  SASS: UBLKCP + SYNCS.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+struct SlabStage {
+  float4 s0[kChunk], s1[kChunk], s2[kChunk];
+};
+
+// Stage `cnt` slab entries starting at global entry `e0` into `dst`.  BULK: thread 0 issues three bulk copies
+// that complete on `bar`; otherwise all threads copy cooperatively (caller synchronises).
+template <bool BULK>
+__device__ __forceinline__ void stage_slab(SlabStage* dst, const float4* __restrict__ s0, const float4* __restrict__ s1,
+                                           const float4* __restrict__ s2, size_t e0, int cnt, uint64_t* bar,
+                                           int nthreads) {
+  if (BULK) {
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)cnt * 16u;
+      mbar_expect_tx(bar, 3u * bytes);
+      bulk_g2s(dst->s0, s0 + e0, bytes, bar);
+      bulk_g2s(dst->s1, s1 + e0, bytes, bar);
+      bulk_g2s(dst->s2, s2 + e0, bytes, bar);
+    }
+  } else {
+    for (int k = threadIdx.x; k < cnt; k += nthreads) {
+      dst->s0[k] = s0[e0 + k];
+      dst->s1[k] = s1[e0 + k];
+      dst->s2[k] = s2[e0 + k];
+    }
+  }
+}
+
+
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+
+// STATS (instrumentation build of the same kernel, gsb_blend_stats): counts warp iterations (= 64 evaluated
+// (pixel, Gaussian) pairs each) and contributing pairs into stats[0..1].
+template <bool BULK, bool STATS = false>
+__global__ void __launch_bounds__(kThreads2, GSB_FWD_MINB)
+k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
+             const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+             float* __restrict__ out_color, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+             unsigned long long* __restrict__ stats = nullptr) {
+  unsigned int st_iter = 0, st_valid = 0;
+  __shared__ __align__(128) SlabStage stg[BULK ? 2 : 1];
+  __shared__ __align__(8) uint64_t bars[2];
+  if (BULK) {
+    if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+  }
+  const int tile = blockIdx.x;
+  const int tx = tile % gx, ty = tile / gx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sx0 = tx * kBlock + (warp & 1) * 8, sy0 = ty * kBlock + (warp >> 1) * 8;
+  const int px = sx0 + (lane & 7), pyA = sy0 + (lane >> 3), pyB = pyA + 4;
+  const bool inA = px < W && pyA < H, inB = px < W && pyB < H;
+  const float fx = (float)px;
+  const float2 fy = f2((float)pyA, (float)pyB);
+  const float rx0 = (float)sx0, rx1 = (float)min(sx0 + 7, W - 1);
+  const float ryA0 = (float)sy0, ryA1 = (float)min(sy0 + 3, H - 1);
+  const float ryB0 = (float)(sy0 + 4), ryB1 = (float)min(sy0 + 7, H - 1);
+  const uint2 rg = ranges[tile];
+  const int n = (int)(rg.y - rg.x);
+  float2 T = f2(1.f, 1.f), Cr = f2(0.f, 0.f), Cg = f2(0.f, 0.f), Cb = f2(0.f, 0.f);
+  uint32_t lastA = 0, lastB = 0;
+  bool doneA = !inA, doneB = !inB;
+  bool wdoneA = !(sx0 < W && sy0 < H), wdoneB = !(sx0 < W && sy0 + 4 < H);
+  const int nch = (n + kChunk - 1) / kChunk;
+  if (BULK && nch > 0) stage_slab<true>(&stg[0], s0, s1, s2, (size_t)rg.x, min(kChunk, n), &bars[0], kThreads2);
+  int pending = -1;    // chunk whose bulk copy is in flight but has not been waited for
+  for (int ci = 0; ci < nch; ++ci) {
+    const int base = ci * kChunk;
+    const int cnt = min(kChunk, n - base);
+    const SlabStage* cur = &stg[BULK ? (ci & 1) : 0];
+    if (BULK) {
+      pending = -1;
+      if (ci + 1 < nch) {     // prefetch the next chunk into the other stage (freed by the barrier below)
+        stage_slab<true>(&stg[(ci + 1) & 1], s0, s1, s2, (size_t)rg.x + base + kChunk, min(kChunk, n - base - kChunk),
+                         &bars[(ci + 1) & 1], kThreads2);
+        pending = ci + 1;
+      }
+      mbar_wait(&bars[ci & 1], (uint32_t)((ci >> 1) & 1));
+    } else {
+      stage_slab<false>(&stg[0], s0, s1, s2, (size_t)rg.x + base, cnt, nullptr, kThreads2);
+      __syncthreads();
+    }
+    const float4* sm0 = cur->s0;
+    const float4* sm1 = cur->s1;
+    const float4* sm2 = cur->s2;
+    if (!(wdoneA && wdoneB)) {
+      for (int b = 0; b < cnt; b += 32) {
+        const int j = b + lane;
+        bool hitA = false, hitB = false;
+        if (j < cnt) {
+          const float4 e0 = sm0[j], e1 = sm1[j];
+          if (!wdoneA) hitA = slab_may_contribute(e0, e1, rx0, ryA0, rx1, ryA1);
+          if (!wdoneB) hitB = slab_may_contribute(e0, e1, rx0, ryB0, rx1, ryB1);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, hitA || hitB);
+        while (mask) {
+          const int k = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float4 e0 = sm0[b + k], e1 = sm1[b + k], c = sm2[b + k];
+          const float dx = e0.x - fx;
+          const float2 dy = f2(e0.y - fy.x, e0.y - fy.y);
+          const float c1 = e0.w * dx, c0 = e0.z * dx * dx;
+          // power' = c0 + dy * (c1 + C' * dy)
+          const float2 pw = __ffma2_rn(dy, __ffma2_rn(f2s(e1.x), dy, f2s(c1)), f2s(c0));
+          const float2 G = f2(ex2_approx(pw.x), ex2_approx(pw.y));
+          float2 al = __fmul2_rn(f2s(e1.y), G);
+          al.x = fminf(0.99f, al.x); al.y = fminf(0.99f, al.y);
+          bool vA = !doneA && pw.x <= 0.f && al.x >= kAlphaMin;
+          bool vB = !doneB && pw.y <= 0.f && al.y >= kAlphaMin;
+          const float2 tT = __fmul2_rn(T, __ffma2_rn(al, f2s(-1.f), f2s(1.f)));
+          if (vA && tT.x < kTEps) { doneA = true; vA = false; }
+          if (vB && tT.y < kTEps) { doneB = true; vB = false; }
+          float2 w = __fmul2_rn(al, T);
+          w.x = vA ? w.x : 0.f; w.y = vB ? w.y : 0.f;
+          Cr = __ffma2_rn(f2s(c.x), w, Cr);
+          Cg = __ffma2_rn(f2s(c.y), w, Cg);
+          Cb = __ffma2_rn(f2s(c.z), w, Cb);
+          const uint32_t pos = (uint32_t)(base + b + k + 1);
+          T.x = vA ? tT.x : T.x; T.y = vB ? tT.y : T.y;
+          lastA = vA ? pos : lastA; lastB = vB ? pos : lastB;
+          if (STATS) { ++st_iter; st_valid += (vA ? 1u : 0u) + (vB ? 1u : 0u); }
+        }
+        wdoneA = __all_sync(0xffffffffu, doneA);
+        wdoneB = __all_sync(0xffffffffu, doneB);
+        if (wdoneA && wdoneB) break;
+      }
+    }
+    if (__syncthreads_and(wdoneA && wdoneB)) break;
+    pending = -1;
+  }
+  if (BULK && pending >= 0) mbar_wait(&bars[pending & 1], (uint32_t)((pending >> 1) & 1));   // never exit with a copy in flight
+  if (STATS) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) st_valid += __shfl_xor_sync(0xffffffffu, st_valid, o);
+    if (lane == 0) { atomicAdd(stats + 0, (unsigned long long)st_iter); atomicAdd(stats + 1, (unsigned long long)st_valid); }
+  }
+  const size_t hw = (size_t)W * H;
+  const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+  if (inA) {
+    size_t pix = (size_t)pyA * W + px;
+    final_T[pix] = T.x; n_contrib[pix] = lastA;
+    out_color[pix] = Cr.x + T.x * b0; out_color[hw + pix] = Cg.x + T.x * b1; out_color[2 * hw + pix] = Cb.x + T.x * b2;
+  }
+  if (inB) {
+    size_t pix = (size_t)pyB * W + px;
+    final_T[pix] = T.y; n_contrib[pix] = lastB;
+    out_color[pix] = Cr.y + T.y * b0; out_color[hw + pix] = Cg.y + T.y * b1; out_color[2 * hw + pix] = Cb.y + T.y * b2;
+  }
+}
+
+template <bool BULK, bool STATS = false>
+__global__ void __launch_bounds__(kThreads2, GSB_BWD_MINB)
+k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
+             const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+             const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
+             const float* __restrict__ dL_dpix, float* __restrict__ dacc,
+             unsigned long long* __restrict__ stats = nullptr) {
+  unsigned int st_iter = 0, st_red = 0, st_valid = 0;
+  __shared__ __align__(128) SlabStage stg[BULK ? 2 : 1];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ int s_bmax;
+  if (BULK && threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  const int tile = blockIdx.x;
+  const int tx = tile % gx, ty = tile / gx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sx0 = tx * kBlock + (warp & 1) * 8, sy0 = ty * kBlock + (warp >> 1) * 8;
+  const int px = sx0 + (lane & 7), pyA = sy0 + (lane >> 3), pyB = pyA + 4;
+  const bool inA = px < W && pyA < H, inB = px < W && pyB < H;
+  const float fx = (float)px;
+  const float2 fy = f2((float)pyA, (float)pyB);
+  const float rx0 = (float)sx0, rx1 = (float)min(sx0 + 7, W - 1);
+  const float ryA0 = (float)sy0, ryA1 = (float)min(sy0 + 3, H - 1);
+  const float ryB0 = (float)(sy0 + 4), ryB1 = (float)min(sy0 + 7, H - 1);
+  const uint2 rg = ranges[tile];
+  const size_t hw = (size_t)W * H;
+  const size_t pixA = (size_t)pyA * W + px, pixB = (size_t)pyB * W + px;
+  const float2 T_final = f2(inA ? final_T[pixA] : 0.f, inB ? final_T[pixB] : 0.f);
+  const int lcA = inA ? (int)n_contrib[pixA] : 0, lcB = inB ? (int)n_contrib[pixB] : 0;
+  float2 dLr = f2(0.f, 0.f), dLg = f2(0.f, 0.f), dLb = f2(0.f, 0.f);
+  if (inA) { dLr.x = dL_dpix[pixA]; dLg.x = dL_dpix[hw + pixA]; dLb.x = dL_dpix[2 * hw + pixA]; }
+  if (inB) { dLr.y = dL_dpix[pixB]; dLg.y = dL_dpix[hw + pixB]; dLb.y = dL_dpix[2 * hw + pixB]; }
+  const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+  const float2 tf_bg = __fmul2_rn(T_final, f2(b0 * dLr.x + b1 * dLg.x + b2 * dLb.x, b0 * dLr.y + b1 * dLg.y + b2 * dLb.y));
+  int wmaxA = lcA, wmaxB = lcB;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wmaxA = max(wmaxA, __shfl_xor_sync(0xffffffffu, wmaxA, o));
+    wmaxB = max(wmaxB, __shfl_xor_sync(0xffffffffu, wmaxB, o));
+  }
+  const int wmax = max(wmaxA, wmaxB);
+  if (threadIdx.x == 0) s_bmax = 0;
+  __syncthreads();
+  if (lane == 0) atomicMax(&s_bmax, wmax);
+  __syncthreads();
+  const int bmax = s_bmax;
+  float2 T = T_final;
+  float2 acc_r = f2(0.f, 0.f), acc_g = f2(0.f, 0.f), acc_b = f2(0.f, 0.f);
+  const int nchunks = (bmax + kChunk - 1) / kChunk;
+  // chunks are visited back to front; it = 0 is the LAST chunk
+  if (BULK && nchunks > 0)
+    stage_slab<true>(&stg[0], s0, s1, s2, (size_t)rg.x + (size_t)(nchunks - 1) * kChunk,
+                     min(kChunk, bmax - (nchunks - 1) * kChunk), &bars[0], kThreads2);
+  for (int it = 0; it < nchunks; ++it) {
+    const int ch = nchunks - 1 - it;
+    const int base = ch * kChunk;
+    const int cnt = min(kChunk, bmax - base);
+    const SlabStage* cur = &stg[BULK ? (it & 1) : 0];
+    if (BULK) {
+      if (it + 1 < nchunks)
+        stage_slab<true>(&stg[(it + 1) & 1], s0, s1, s2, (size_t)rg.x + base - kChunk, kChunk, &bars[(it + 1) & 1],
+                         kThreads2);
+      mbar_wait(&bars[it & 1], (uint32_t)((it >> 1) & 1));
+    } else {
+      stage_slab<false>(&stg[0], s0, s1, s2, (size_t)rg.x + base, cnt, nullptr, kThreads2);
+      __syncthreads();
+    }
+    const float4* sm0 = cur->s0;
+    const float4* sm1 = cur->s1;
+    const float4* sm2 = cur->s2;
+    if (base < wmax) {
+      for (int b = (cnt - 1) & ~31; b >= 0; b -= 32) {
+        if (base + b >= wmax) continue;
+        const int j = b + lane;
+        bool hit = false;
+        if (j < cnt) {
+          const float4 e0 = sm0[j], e1 = sm1[j];
+          if (base + j < wmaxA) hit = slab_may_contribute(e0, e1, rx0, ryA0, rx1, ryA1);
+          if (!hit && base + j < wmaxB) hit = slab_may_contribute(e0, e1, rx0, ryB0, rx1, ryB1);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+          const int k = 31 - __clz(mask);
+          mask &= ~(1u << k);
+          const int pos = base + b + k;
+          const float4 e0 = sm0[b + k], e1 = sm1[b + k];
+          const float dx = e0.x - fx;
+          const float2 dy = f2(e0.y - fy.x, e0.y - fy.y);
+          const float c1 = e0.w * dx, c0 = e0.z * dx * dx;
+          const float2 pw = __ffma2_rn(dy, __ffma2_rn(f2s(e1.x), dy, f2s(c1)), f2s(c0));
+          const float2 G = f2(ex2_approx(pw.x), ex2_approx(pw.y));
+          float2 al = __fmul2_rn(f2s(e1.y), G);
+          al.x = fminf(0.99f, al.x); al.y = fminf(0.99f, al.y);
+          const bool vA = inA && pos < lcA && pw.x <= 0.f && al.x >= kAlphaMin;
+          const bool vB = inB && pos < lcB && pw.y <= 0.f && al.y >= kAlphaMin;
+          if (STATS) { ++st_iter; st_valid += (vA ? 1u : 0u) + (vB ? 1u : 0u); }
+          if (!__any_sync(0xffffffffu, vA || vB)) continue;
+          if (STATS) ++st_red;
+          const float4 c = sm2[b + k];
+          // masked alpha: an invalid pixel behaves as alpha = 0 (T, accumulator and gradients unchanged)
+          const float2 am = f2(vA ? al.x : 0.f, vB ? al.y : 0.f);
+          const float2 one_m = __ffma2_rn(am, f2s(-1.f), f2s(1.f));
+          const float2 inv = f2(rcp_approx(one_m.x), rcp_approx(one_m.y));
+          T = __fmul2_rn(T, inv);
+          const float2 dcol = __fmul2_rn(am, T);                 // dchannel/dcolor = alpha * T
+          // acc = colour composited from everything BEHIND this entry (the reference's accum_rec);
+          // dL/dalpha = T * sum_ch (c - acc) dL_ch  -  T_final/(1-alpha) * bg.dL ; then acc += alpha (c - acc)
+          const float2 d_r = __fadd2_rn(f2s(c.x), f2(-acc_r.x, -acc_r.y));
+          const float2 d_g = __fadd2_rn(f2s(c.y), f2(-acc_g.x, -acc_g.y));
+          const float2 d_b = __fadd2_rn(f2s(c.z), f2(-acc_b.x, -acc_b.y));
+          float2 da = __ffma2_rn(d_b, dLb, __ffma2_rn(d_g, dLg, __fmul2_rn(d_r, dLr)));
+          da = __fmul2_rn(da, T);
+          da = __ffma2_rn(f2(-tf_bg.x, -tf_bg.y), inv, da);
+          da.x = vA ? da.x : 0.f; da.y = vB ? da.y : 0.f;
+          acc_r = __ffma2_rn(am, d_r, acc_r);
+          acc_g = __ffma2_rn(am, d_g, acc_g);
+          acc_b = __ffma2_rn(am, d_b, acc_b);
+          const float2 dG = __fmul2_rn(f2s(e1.y), da);           // dL/dG = opacity * dL/dalpha
+          const float2 gdG = __fmul2_rn(G, dG);                  // G * dL/dG
+          const float2 gy = __fmul2_rn(gdG, dy);                 // G dL/dG dy
+          const float gxs = (gdG.x + gdG.y) * dx;                // sum over the two pixels of G dL/dG dx
+          const float gys = gy.x + gy.y;
+          float v[9];
+          v[0] = kLn2 * (2.f * gxs * e0.z + gys * e0.w);
+          v[1] = kLn2 * (2.f * gys * e1.x + gxs * e0.w);
+          v[2] = -0.5f * gxs * dx;
+          v[3] = -dx * gys;
+          v[4] = -0.5f * (gy.x * dy.x + gy.y * dy.y);
+          v[5] = G.x * da.x + G.y * da.y;
+          const float dcs_r = dcol.x * dLr.x + dcol.y * dLr.y;
+          v[6] = dcs_r;
+          v[7] = dcol.x * dLg.x + dcol.y * dLg.y;
+          v[8] = dcol.x * dLb.x + dcol.y * dLb.y;
+          warp_reduce9(v, lane);
+          const float a1 = __shfl_down_sync(0xffffffffu, v[0], 4);
+          const float a2 = __shfl_down_sync(0xffffffffu, v[0], 8);
+          const float a3 = __shfl_down_sync(0xffffffffu, v[0], 12);
+          float* dst = dacc + (size_t)__float_as_uint(e1.w) * 12;
+          if (!STATS) {
+            if ((lane & 15) == 0) red_add_v4(dst + (lane >> 2), v[0], a1, a2, a3);
+            if (lane == 1) atomicAdd(dst + 8, v[8]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (STATS) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) st_valid += __shfl_xor_sync(0xffffffffu, st_valid, o);
+    if (lane == 0) {
+      atomicAdd(stats + 2, (unsigned long long)st_iter);
+      atomicAdd(stats + 3, (unsigned long long)st_valid);
+      atomicAdd(stats + 4, (unsigned long long)st_red);
+    }
+  }
+}
+
+
+}  // namespace
+
+int gsb_launch_blend_fwd(const BinView& bv, const ImgView& iv, const float* bg, int W, int H, float* out_color,
+                         cudaStream_t st) {
+  const int gx = (W + kBlock - 1) / kBlock, gy = (H + kBlock - 1) / kBlock;
+  ProfScope ps(GSB_K_BLEND_FWD, st);
+  const int ver = gsb_option_blend_version(), bulk = gsb_option_stage_bulk();
+  if (ver == 2 && bulk)
+    k_blend_fwd2<true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, out_color,
+                                                      iv.final_T, iv.n_contrib);
+  else if (ver == 2)
+    k_blend_fwd2<false><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, out_color,
+                                                       iv.final_T, iv.n_contrib);
+  else
+    k_blend_fwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, out_color, iv.final_T,
+                                              iv.n_contrib);
+  GSB_CUDA(cudaGetLastError());
+  return GSB_OK;
+}
+
+int gsb_launch_blend_bwd(const BinView& bv, const ImgView& iv, const float* bg, int W, int H, const float* dL_dout,
+                         float* dacc, cudaStream_t st) {
+  const int gx = (W + kBlock - 1) / kBlock, gy = (H + kBlock - 1) / kBlock;
+  ProfScope ps(GSB_K_BLEND_BWD, st);
+  const int ver = gsb_option_blend_version(), bulk = gsb_option_stage_bulk();
+  if (ver == 2 && bulk)
+    k_blend_bwd2<true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, iv.final_T,
+                                                      iv.n_contrib, dL_dout, dacc);
+  else if (ver == 2)
+    k_blend_bwd2<false><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, iv.final_T,
+                                                       iv.n_contrib, dL_dout, dacc);
+  else
+    k_blend_bwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, iv.final_T, iv.n_contrib,
+                                              dL_dout, dacc);
+  GSB_CUDA(cudaGetLastError());
+  return GSB_OK;
+}
+
+// Instrumentation (bench.py roofline block): re-runs the v2 blend kernels on the buffers of the last forward /
+// backward with counters on.  stats (device, 8 x u64, zeroed here): [0] forward warp iterations (64 evaluated
+// pairs each), [1] forward contributing pairs, [2] backward warp iterations, [3] backward contributing pairs,
+// [4] backward warp iterations that reached the gradient reduction.  The forward pass rewrites identical outputs;
+// the backward pass (run only if dL_dout != NULL) issues no atomics.
+extern "C" GSB_API int gsb_blend_stats(const GsbCamera* cam, int32_t P, void* geom, void* binning, int64_t R,
+                                       void* image, float* out_color, const float* dL_dout,
+                                       unsigned long long* stats, gsb_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  GSB_REQUIRE(cam && geom && binning && image && out_color && stats, "null buffer");
+  const int W = cam->width, H = cam->height;
+  const int gx = (W + kBlock - 1) / kBlock, gy = (H + kBlock - 1) / kBlock;
+  GeomView gv = geom_view(geom, P);
+  BinView bv = bin_view(binning, R, W, H);
+  ImgView iv = img_view(image, W, H);
+  GSB_CUDA(cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), st));
+  k_blend_fwd2<true, true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, out_color,
+                                                          iv.final_T, iv.n_contrib, stats);
+  if (dL_dout)
+    k_blend_bwd2<true, true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, iv.final_T,
+                                                            iv.n_contrib, dL_dout, (float*)gv.dacc, stats);
+  GSB_CUDA(cudaGetLastError());
+  return GSB_OK;
+}

@@ -75,7 +75,9 @@ __device__ __forceinline__ void adam1(const Piece& t, bool gate, float lr_mul, f
 }
 
 template <int WORLD>
-__global__ void __launch_bounds__(kFT) k_fused_rs_adam_ag(FusedArgs a, const unsigned int* __restrict__ flags) {
+__global__ void __launch_bounds__(kFT) k_fused_rs_adam_ag(FusedArgs a, const unsigned int* __restrict__ flags,
+                                                          const unsigned int* __restrict__ skip) {
+  if (skip && *skip) return;      // some rank's forward overflowed its binning buffer: nobody updates
   int k = 0;
 #pragma unroll
   for (int i = 1; i < kMaxPieces; ++i)
@@ -160,7 +162,8 @@ extern "C" GSB_API int gsb_ipc_free(void* dev_ptr) {
 extern "C" GSB_API int gsb_fused_rs_adam_ag(int32_t world, int32_t rank, const float* const* peer_grads,
                                             float* const* peer_params, float* exp_avg_shard, float* exp_avg_sq_shard,
                                             int64_t shard_begin, int32_t n_pieces, const GsbShardPiece* pieces,
-                                            const uint32_t* flags, float grad_scale, gsb_stream_t stream_) {
+                                            const uint32_t* flags, const uint32_t* skip_if_nonzero, float grad_scale,
+                                            gsb_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || !peer_grads || !peer_params || !exp_avg_shard ||
       !exp_avg_sq_shard || n_pieces < 0 || n_pieces > kMaxPieces || (n_pieces > 0 && !pieces) || !flags ||
@@ -201,13 +204,13 @@ extern "C" GSB_API int gsb_fused_rs_adam_ag(int32_t world, int32_t rank, const f
   gsb_count_launch(1);
   int slot = gsb_prof_begin(GSB_K_ADAM, st);
   switch (world) {
-    case 2: k_fused_rs_adam_ag<2><<<nb, kFT, 0, st>>>(a, flags); break;
-    case 3: k_fused_rs_adam_ag<3><<<nb, kFT, 0, st>>>(a, flags); break;
-    case 4: k_fused_rs_adam_ag<4><<<nb, kFT, 0, st>>>(a, flags); break;
-    case 5: k_fused_rs_adam_ag<5><<<nb, kFT, 0, st>>>(a, flags); break;
-    case 6: k_fused_rs_adam_ag<6><<<nb, kFT, 0, st>>>(a, flags); break;
-    case 7: k_fused_rs_adam_ag<7><<<nb, kFT, 0, st>>>(a, flags); break;
-    default: k_fused_rs_adam_ag<8><<<nb, kFT, 0, st>>>(a, flags); break;
+    case 2: k_fused_rs_adam_ag<2><<<nb, kFT, 0, st>>>(a, flags, skip_if_nonzero); break;
+    case 3: k_fused_rs_adam_ag<3><<<nb, kFT, 0, st>>>(a, flags, skip_if_nonzero); break;
+    case 4: k_fused_rs_adam_ag<4><<<nb, kFT, 0, st>>>(a, flags, skip_if_nonzero); break;
+    case 5: k_fused_rs_adam_ag<5><<<nb, kFT, 0, st>>>(a, flags, skip_if_nonzero); break;
+    case 6: k_fused_rs_adam_ag<6><<<nb, kFT, 0, st>>>(a, flags, skip_if_nonzero); break;
+    case 7: k_fused_rs_adam_ag<7><<<nb, kFT, 0, st>>>(a, flags, skip_if_nonzero); break;
+    default: k_fused_rs_adam_ag<8><<<nb, kFT, 0, st>>>(a, flags, skip_if_nonzero); break;
   }
   gsb_prof_end(slot, st);
   cudaError_t e = cudaGetLastError();

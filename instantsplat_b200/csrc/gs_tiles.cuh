@@ -1,0 +1,101 @@
+// Tile coverage of one projected Gaussian: the ONE definition of "which 16x16 tiles receive this splat",
+// used twice -- by k_preprocess to COUNT instances per Gaussian and per tile, and by k_scatter to EMIT them.
+// Coverage = the reference's tile rect minus the tiles that the lossless cull
+// (gs_math.cuh rect_may_contribute) proves cannot reach alpha >= 1/255.
+//
+// The emit side never trusts the two evaluations to agree bit for bit: an instance is written only while the
+// tile's cursor is below the counted length (and below the buffer capacity), and the consumer uses
+// min(count, cursor) as the list length.  A borderline tile that flips between the two passes carries no
+// visible contribution by construction of the cull margin, so dropping / missing it does not change the image.
+#pragma once
+#include "gs_math.cuh"
+
+namespace gsb {
+
+constexpr int kCoopTiles = 24;   // rects larger than this are walked by the whole warp
+
+struct TileSink {
+  // count mode: tcount != nullptr, pairs == nullptr
+  // emit  mode: pairs  != nullptr
+  uint32_t* tcount;
+  const uint32_t* tstart;
+  uint32_t* tcursor;
+  unsigned long long* pairs;
+  uint32_t cap;
+};
+
+__device__ __forceinline__ void sink_tile(const TileSink& s, uint32_t tile, unsigned long long key) {
+  if (s.pairs) {
+    const uint32_t pos = atomicAdd(s.tcursor + tile, 1u);
+    if (pos < s.tcount[tile]) {
+      const uint32_t dst = s.tstart[tile] + pos;
+      if (dst < s.cap) s.pairs[dst] = key;
+    }
+  } else {
+    atomicAdd(s.tcount + tile, 1u);
+  }
+}
+
+struct SplatRect {
+  float x, y, A, B, C, qthr;
+  int rx0, ry0, rx1, ry1;
+};
+
+__device__ __forceinline__ bool tile_kept(const SplatRect& p, int tx, int ty, int W, int H, bool cull) {
+  if (!cull) return true;
+  const float x0 = (float)(tx * kBlock), y0 = (float)(ty * kBlock);
+  const float x1 = fminf(x0 + kBlock - 1, (float)(W - 1)), y1 = fminf(y0 + kBlock - 1, (float)(H - 1));
+  return rect_may_contribute(p.x, p.y, p.A, p.B, p.C, p.qthr, x0, y0, x1, y1);
+}
+
+// one thread walks its own (small) rect; returns the number of kept tiles
+__device__ __forceinline__ uint32_t visit_tiles(const SplatRect& p, int W, int H, int gx, bool cull,
+                                                const TileSink& s, unsigned long long key) {
+  uint32_t n = 0;
+  for (int ty = p.ry0; ty < p.ry1; ++ty)
+    for (int tx = p.rx0; tx < p.rx1; ++tx)
+      if (tile_kept(p, tx, ty, W, H, cull)) {
+        sink_tile(s, (uint32_t)(ty * gx + tx), key);
+        ++n;
+      }
+  return n;
+}
+
+// Gaussians whose rect spans more than kCoopTiles tiles are walked by the WHOLE WARP (one tile per lane per
+// step) instead of one thread looping over up to thousands of tiles -- the per-thread loop is a performance
+// cliff once a few Gaussians grow large.  Must be called by all 32 lanes; `mine` says whether this lane's
+// Gaussian wants the cooperative path.  Returns the lane's kept-tile count.
+__device__ __forceinline__ uint32_t visit_tiles_coop(bool mine, const SplatRect& p, int W, int H, int gx, bool cull,
+                                                     const TileSink& s, unsigned long long key) {
+  const int lane = threadIdx.x & 31;
+  uint32_t result = 0;
+  unsigned big = __ballot_sync(0xffffffffu, mine);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    SplatRect b;
+    b.x = __shfl_sync(0xffffffffu, p.x, src); b.y = __shfl_sync(0xffffffffu, p.y, src);
+    b.A = __shfl_sync(0xffffffffu, p.A, src); b.B = __shfl_sync(0xffffffffu, p.B, src);
+    b.C = __shfl_sync(0xffffffffu, p.C, src); b.qthr = __shfl_sync(0xffffffffu, p.qthr, src);
+    b.rx0 = __shfl_sync(0xffffffffu, p.rx0, src); b.rx1 = __shfl_sync(0xffffffffu, p.rx1, src);
+    b.ry0 = __shfl_sync(0xffffffffu, p.ry0, src); b.ry1 = __shfl_sync(0xffffffffu, p.ry1, src);
+    const unsigned long long bkey = __shfl_sync(0xffffffffu, key, src);
+    const int w = b.rx1 - b.rx0, n = w * (b.ry1 - b.ry0);
+    uint32_t run = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      bool keep = false;
+      int tx = 0, ty = 0;
+      if (i < n) {
+        ty = b.ry0 + i / w; tx = b.rx0 + i - (i / w) * w;
+        keep = tile_kept(b, tx, ty, W, H, cull);
+      }
+      if (keep) sink_tile(s, (uint32_t)(ty * gx + tx), bkey);
+      run += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    if (lane == src) result = run;
+  }
+  return result;
+}
+
+}  // namespace gsb

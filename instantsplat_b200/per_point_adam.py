@@ -14,9 +14,10 @@ from . import _lib
 from ._lib import ADAM_MAX_TENSORS, GsbAdamTensor, check
 
 
-def launch_adam(entries, flags):
+def launch_adam(entries, flags, skip_ptr=None):
     """entries: list of dicts(param, grad, exp_avg, exp_avg_sq, per_point_lr, step_size, beta1, beta2,
-    eps, weight_decay, grad_scale, row_len)."""
+    eps, weight_decay, grad_scale, row_len).  skip_ptr: optional device address of a word that, when non-zero,
+    makes the device skip the whole update (gsb_adam_step_gated)."""
     L = _lib.lib()
     for i in range(0, len(entries), ADAM_MAX_TENSORS):
         chunk = entries[i:i + ADAM_MAX_TENSORS]
@@ -30,7 +31,7 @@ def launch_adam(entries, flags):
             t.grad_scale = float(e.get("grad_scale", 1.0))
             t.step_size, t.beta1, t.beta2 = float(e["step_size"]), float(e["beta1"]), float(e["beta2"])
             t.eps, t.weight_decay = float(e["eps"]), float(e["weight_decay"])
-        check(L.gsb_adam_step(len(chunk), arr, flags.data_ptr(), _lib.stream_ptr()), "gsb_adam_step")
+        check(L.gsb_adam_step_gated(len(chunk), arr, flags.data_ptr(), skip_ptr, _lib.stream_ptr()), "gsb_adam_step")
 
 
 def _validated_multiplier(param: torch.Tensor, mult):

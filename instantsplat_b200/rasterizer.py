@@ -8,6 +8,8 @@ same names, argument meaning and error behaviour.
 from __future__ import annotations
 
 import ctypes
+import warnings
+import weakref
 from typing import NamedTuple, Optional
 
 import torch
@@ -34,24 +36,46 @@ class GaussianRasterizationSettings(NamedTuple):
     debug: bool
 
 
-_pinned = {}
-
-
-def _pinned_u32(device) -> torch.Tensor:
-    key = (device.index, torch.cuda.current_stream().cuda_stream)
-    t = _pinned.get(key)
-    if t is None:
-        t = torch.zeros(1, dtype=torch.int32).pin_memory()
-        _pinned[key] = t
-    return t
-
-
 EXACT_CULL = True   # lossless alpha<1/255 tile culling (set False for the reference's rect-only binning)
+
+# The instance count R (number of (Gaussian, tile) pairs) never has to reach the host: the kernels read it from
+# device memory.  The host only chooses the CAPACITY of the binning buffer.  SYNC_FREE = True sizes it from the
+# last count seen for the same (device, P, W, H) with 50 % headroom and verifies lazily (at the backward, or at
+# the next forward) that it was enough; the very first call of a shape -- and every call when SYNC_FREE is False
+# -- waits for R once and sizes the buffer exactly, like the reference's blocking cudaMemcpy of num_rendered.
+SYNC_FREE = True
+HEADROOM = 1.5
+_last_R = {}            # (device index, P, W, H) -> last verified instance count
+_pending = {}           # same key -> _State whose capacity check has not been read yet
+
+
+class _StatusRing:
+    """Pinned 4-word status slots, recycled round-robin (a slot is long verified before it comes round again)."""
+
+    def __init__(self, n=512):
+        self.buf = torch.zeros(n, 4, dtype=torch.int32).pin_memory()
+        self.n, self.i = n, 0
+
+    def take(self) -> torch.Tensor:
+        t = self.buf[self.i]
+        self.i = (self.i + 1) % self.n
+        return t
+
+
+_ring = None
+
+
+def _status_slot() -> torch.Tensor:
+    global _ring
+    if _ring is None:
+        _ring = _StatusRing()
+    return _ring.take()
 
 
 class _State:
     """Everything the backward needs; keeps the torch buffers alive."""
-    __slots__ = ("cam", "g", "geom", "binning", "image", "R", "keep", "P", "M", "packed", "has_pose")
+    __slots__ = ("cam", "g", "geom", "binning", "image", "R", "keep", "P", "M", "packed", "has_pose",
+                 "key", "status", "event", "checked", "color", "bin_bytes", "R_true", "__weakref__")
 
 
 def _camera(settings: GaussianRasterizationSettings, sh_coeffs: int, keep: list) -> GsbCamera:
@@ -66,6 +90,66 @@ def _camera(settings: GaussianRasterizationSettings, sh_coeffs: int, keep: list)
     cam.exact_cull = 1 if EXACT_CULL else 0
     cam.bg, cam.viewmatrix, cam.projmatrix, cam.campos = ptr(bg), ptr(vm), ptr(pm), ptr(cp)
     return cam
+
+
+def _render_phase(st: _State, cap: int, dev):
+    """Binning + blend into st.color with a binning buffer of `cap` instances (allocation rounded up to 32 MiB so
+    the caching allocator can reuse the block of the previous call)."""
+    L = _lib.lib()
+    H, W = st.cam.height, st.cam.width
+    bin_bytes = (L.gsb_binning_bytes(cap, W, H) + (1 << 25) - 1) >> 25 << 25
+    st.binning = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
+    st.bin_bytes, st.R = bin_bytes, cap
+    st.status = _status_slot()
+    check(L.gsb_render(ctypes.byref(st.cam), st.P, st.geom.data_ptr(), st.binning.data_ptr(), bin_bytes, cap,
+                       st.image.data_ptr(), st.color.data_ptr(), st.status.data_ptr(), _lib.stream_ptr()),
+          "gsb_render")
+    st.event = torch.cuda.Event()
+    st.event.record()
+    st.checked = False
+
+
+def _note_R(key, R: int) -> None:
+    """Capacity estimate = slowly decaying maximum of the counts seen (different views share a key)."""
+    _last_R[key] = max(R, int(0.98 * _last_R.get(key, 0)))
+
+
+def _verify(st: _State, dev) -> None:
+    """Read the lazily copied status words of st's forward; if the binning buffer was too small, redo the render
+    phase in place with an exactly sized one (image and scratch become exact before anybody differentiates)."""
+    if st.checked:
+        return
+    st.event.synchronize()
+    R_true, overflow = int(st.status[0]) & 0xFFFFFFFF, int(st.status[1])
+    _note_R(st.key, R_true)
+    st.checked, st.R_true = True, R_true
+    _pending.pop(st.key, None)
+    if overflow:
+        warnings.warn(f"instantsplat_b200: instance count {R_true} exceeded the binning capacity {st.R}; "
+                      "the render phase was repeated with an exact buffer", RuntimeWarning)
+        with torch.cuda.device(dev):
+            _render_phase(st, R_true, dev)
+            st.event.synchronize()
+            st.checked = True
+
+
+def _verify_pending(key, dev) -> None:
+    """At the next forward of the same shape: settle the previous call's capacity check (its result has long
+    arrived; the forward's state may already be gone if nobody differentiated it)."""
+    rec = _pending.pop(key, None)
+    if rec is None:
+        return
+    ref, status, event, cap = rec
+    st = ref()
+    if st is not None:
+        _pending[key] = rec
+        _verify(st, dev)
+        return
+    event.synchronize()
+    _note_R(key, int(status[0]) & 0xFFFFFFFF)
+    if int(status[1]):
+        warnings.warn(f"instantsplat_b200: a forward-only call rendered with a truncated binning buffer "
+                      f"({_last_R[key]} instances > capacity {cap}); the capacity has been raised", RuntimeWarning)
 
 
 def _forward(settings, means3D, scales, rotations, opacities, sh_dc, sh_rest, sh_packed, M,
@@ -88,26 +172,35 @@ def _forward(settings, means3D, scales, rotations, opacities, sh_dc, sh_rest, sh
         setattr(g, k, ptr(v))
     st.g, st.P, st.M, st.packed, st.has_pose = g, P, M, bool(sh_packed), pose is not None
     H, W = st.cam.height, st.cam.width
-    stream = _lib.stream_ptr()
-    geom_bytes = L.gsb_geom_bytes(P)
-    st.geom = torch.empty(geom_bytes, dtype=torch.uint8, device=dev)
-    radii = torch.empty(P, dtype=torch.int32, device=dev)
-    host_r = _pinned_u32(dev)
-    check(L.gsb_preprocess(ctypes.byref(st.cam), ctypes.byref(g), st.geom.data_ptr(), geom_bytes,
-                           radii.data_ptr(), host_r.data_ptr(), stream), "gsb_preprocess")
-    torch.cuda.current_stream().synchronize()          # the one host sync: R sizes the binning buffers
-    R = int(host_r.item()) & 0xFFFFFFFF
-    st.R = R
-    # round the R-dependent request up to 32 MiB so the caching allocator can reuse the block of the previous call
-    bin_bytes = (L.gsb_binning_bytes(R, W, H) + (1 << 25) - 1) >> 25 << 25
-    st.binning = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
-    st.image = torch.empty(L.gsb_image_bytes(W, H), dtype=torch.uint8, device=dev)
-    color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
-    check(L.gsb_render(ctypes.byref(st.cam), P, st.geom.data_ptr(), st.binning.data_ptr(), bin_bytes, R,
-                       st.image.data_ptr(), color.data_ptr(), stream), "gsb_render")
-    if settings.debug:
-        torch.cuda.synchronize()
-    return color, radii, st
+    st.key = (dev.index, P, W, H)
+    with torch.cuda.device(dev):
+        _verify_pending(st.key, dev)   # long finished in practice: just reads the pinned words
+        stream = _lib.stream_ptr()
+        geom_bytes = L.gsb_geom_bytes(P)
+        st.geom = torch.empty(geom_bytes, dtype=torch.uint8, device=dev)
+        radii = torch.empty(P, dtype=torch.int32, device=dev)
+        st.image = torch.empty(L.gsb_image_bytes(W, H), dtype=torch.uint8, device=dev)
+        st.color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
+        est = _last_R.get(st.key) if (SYNC_FREE and not settings.debug) else None
+        if est is None:
+            host = _status_slot()
+            check(L.gsb_preprocess(ctypes.byref(st.cam), ctypes.byref(g), st.geom.data_ptr(), geom_bytes,
+                                   radii.data_ptr(), host.data_ptr(), stream), "gsb_preprocess")
+            torch.cuda.current_stream().synchronize()      # exact sizing: wait for R once
+            cap = int(host[0]) & 0xFFFFFFFF
+        else:
+            check(L.gsb_preprocess(ctypes.byref(st.cam), ctypes.byref(g), st.geom.data_ptr(), geom_bytes,
+                                   radii.data_ptr(), None, stream), "gsb_preprocess")
+            cap = int(est * HEADROOM) + 65536
+        _render_phase(st, cap, dev)
+        if est is None:
+            _note_R(st.key, cap)
+            st.checked, st.R_true = True, cap
+        else:
+            _pending[st.key] = (weakref.ref(st), st.status, st.event, cap)
+        if settings.debug:
+            torch.cuda.synchronize()
+    return st.color, radii, st
 
 
 def _backward(st: _State, dL_dout, want, dev):
@@ -116,6 +209,7 @@ def _backward(st: _State, dL_dout, want, dev):
     /root/reference/render.py:99-170 passes {"pose"}).  Returns dict of dense grad tensors."""
     L = _lib.lib()
     P, M = st.P, st.M
+    _verify(st, dev)
     dL = f32c(dL_dout)
     gr = GsbGrads()
     out = {}
@@ -166,6 +260,10 @@ class _RasterizeGaussians(torch.autograd.Function):
             sh if has(sh) else None, None, 1, M, colors_precomp if has(colors_precomp) else None,
             cov3Ds_precomp if has(cov3Ds_precomp) else None, None, 0)
         ctx.st = st
+        # registered only so that autograd's version counters catch in-place edits between forward and backward
+        # (the backward re-projects from the live input buffers)
+        ctx.save_for_backward(*[t for t in (means3D, sh, colors_precomp, opacities, scales, rotations,
+                                            cov3Ds_precomp) if torch.is_tensor(t)])
         ctx.shapes = (opacities.shape,)
         ctx.debug = raster_settings.debug
         ctx.mark_non_differentiable(radii)
@@ -174,6 +272,7 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out_color, _grad_radii):
         st = ctx.st
+        _ = ctx.saved_tensors
         g = _backward(st, grad_out_color, None, grad_out_color.device)
         if ctx.debug:
             torch.cuda.synchronize()
@@ -198,6 +297,7 @@ class _RasterizeFused(torch.autograd.Function):
         color, radii, st = _forward(raster_settings, xyz, scaling, rotation, opacity.reshape(-1),
                                     f_dc.reshape(-1, 3), f_rest if M > 1 else None, 0, M, None, None, pose, 1)
         ctx.st = st
+        ctx.save_for_backward(*[t for t in (xyz, rotation, scaling, opacity, f_dc, f_rest, pose) if torch.is_tensor(t)])
         ctx.shapes = (opacity.shape, f_dc.shape, None if f_rest is None else f_rest.shape)
         ctx.mark_non_differentiable(radii)
         return color, radii
@@ -205,6 +305,7 @@ class _RasterizeFused(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out_color, _grad_radii):
         st = ctx.st
+        _ = ctx.saved_tensors
         need = ctx.needs_input_grad      # xyz, rotation, scaling, opacity, f_dc, f_rest, pose, means2D, settings
         names = ("means3D", "rotations", "scales", "opacities", "sh_dc", "sh_rest", "pose", "means2D")
         want = {n for n, k in zip(names, need) if k}

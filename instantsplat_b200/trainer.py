@@ -65,6 +65,8 @@ class OptimConfig:
     pp_optimizer = True
     optim_pose = True
     spatial_lr_scale = 1.0
+    sh_increase_interval = 1000      # train.py:146-147: oneupSHdegree() when iteration % 1000 == 0
+    max_sh_degree = 3
 
 
 def _align(n, a=64):
@@ -111,8 +113,13 @@ class JointTrainer:
         for name, k in SEGMENTS:
             self.view(self.params, name).copy_(scene.params[name].reshape(P, k).to(self.dev))
         self.poses = scene.poses.to(self.dev).float().contiguous()              # [n_views,7]
-        self.pose_grad = (self._xch[8:].view(scene.n_views, 7) if self.exchange == "fused_p2p"
-                          else torch.zeros_like(self.poses))
+        if self.exchange == "fused_p2p":
+            self.pose_grad = self._xch[8:].view(scene.n_views, 7)
+            self._pg_buf = None
+        else:
+            # [n_views*7] pose gradients + 1 word carrying this rank's binning-overflow flag through the all-reduce
+            self._pg_buf = torch.zeros(scene.n_views * 7 + 1, dtype=torch.float32, device=self.dev)
+            self.pose_grad = self._pg_buf[:-1].view(scene.n_views, 7)
         self.pose_m = torch.zeros_like(self.poses)
         self.pose_v = torch.zeros_like(self.poses)
         self.per_point_lr = None
@@ -135,18 +142,29 @@ class JointTrainer:
         self.image_buf = torch.empty(L.gsb_image_bytes(self.W, self.H), dtype=torch.uint8, device=self.dev)
         self.binning = None
         self.bin_bytes = 0
+        self.cap = 0                  # instance capacity of the binning buffer (0: not sized yet)
+        self.headroom = 1.5
         self.radii = torch.empty(P, dtype=torch.int32, device=self.dev)
         self.color = torch.empty(3, self.H, self.W, dtype=torch.float32, device=self.dev)
         self.dL_dimg = torch.empty_like(self.color)
         self.maps = torch.empty(3, 3, self.H, self.W, dtype=torch.float32, device=self.dev)
         self.sums = torch.zeros(2, dtype=torch.float64, device=self.dev)
-        self.host_r = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.host_status = torch.zeros(2, 4, dtype=torch.int32).pin_memory()   # [0] after preprocess, [1] after render
+        self._ev_pre = torch.cuda.Event()
+        self._status_dev = L.gsb_status_device(self.geom.data_ptr(), P)        # device address of the status words
+        so = self._status_dev - self.geom.data_ptr()
+        self._status_t = self.geom[so:so + 32].view(torch.int32)               # [R, overflow, longest list, ...]
+        self._ovf = None
         self.flags = torch.zeros(8, dtype=torch.int32, device=self.dev)
         self._pose_flags = torch.zeros(8, dtype=torch.int32, device=self.dev)
-        self.iteration = 0
+        if world_size > 1:    # the word the optimizer kernels test: overflow flags summed over the ranks
+            self._ovf = self.flags[7:8] if self.exchange == "fused_p2p" else self._pg_buf[-1:]
+        self.iteration = 0            # reference iterations = views consumed (by all ranks)
         self.opt_step = 0
         self.last_R = 0
+        self.overflows = 0
         self.exact_cull = True
+        self.active_sh_degree = min(scene.sh_degree, self.cfg.max_sh_degree)
         c = self.cfg
         self.xyz_sched = get_expon_lr_func(c.position_lr_init * c.spatial_lr_scale,
                                            c.position_lr_final * c.spatial_lr_scale,
@@ -170,7 +188,7 @@ class JointTrainer:
         cam = GsbCamera()
         cam.width, cam.height = self.W, self.H
         cam.tanfovx, cam.tanfovy, cam.scale_modifier = self.tanfovx, self.tanfovy, 1.0
-        cam.sh_degree, cam.sh_coeffs = self.sh_degree, 16
+        cam.sh_degree, cam.sh_coeffs = self.active_sh_degree, 16
         cam.exact_cull = 1 if self.exact_cull else 0
         cam.bg, cam.viewmatrix = self.bg.data_ptr(), self.viewmatrix.data_ptr()
         cam.projmatrix, cam.campos = self.projmatrix.data_ptr(), self.campos.data_ptr()
@@ -190,23 +208,50 @@ class JointTrainer:
         return g
 
     # ------------------------------------------------------------------------------------------
-    def render(self, view: int) -> torch.Tensor:
-        """Forward only (also the first half of step())."""
+    def _size_binning(self, R: int) -> None:
+        L = _lib.lib()
+        self.cap = int(R * self.headroom) + 65536
+        self.bin_bytes = L.gsb_binning_bytes(self.cap, self.W, self.H)
+        self.binning = torch.empty(self.bin_bytes, dtype=torch.uint8, device=self.dev)
+
+    def _launch_forward(self, view: int) -> None:
+        """Enqueue the forward without ever waiting for the GPU: the instance count R stays on the device; the
+        host only provides a capacity (sized from the counts seen so far, +50 %) and reads R back lazily."""
         L = _lib.lib()
         st = _lib.stream_ptr()
         cam, g = self._cam(), self._gauss(view)
         check(L.gsb_preprocess(ctypes.byref(cam), ctypes.byref(g), self.geom.data_ptr(), self.geom_bytes,
-                               self.radii.data_ptr(), self.host_r.data_ptr(), st), "gsb_preprocess")
-        torch.cuda.current_stream().synchronize()
-        R = int(self.host_r.item()) & 0xFFFFFFFF
-        self.last_R = R
-        need = L.gsb_binning_bytes(R, self.W, self.H)
-        if need > self.bin_bytes:
-            self.bin_bytes = int(need * 1.25)
-            self.binning = torch.empty(self.bin_bytes, dtype=torch.uint8, device=self.dev)
+                               self.radii.data_ptr(), self.host_status[0].data_ptr(), st), "gsb_preprocess")
+        self._ev_pre.record()
+        if self.cap == 0:                                   # very first forward: size the buffer from the real count
+            self._ev_pre.synchronize()
+            self._size_binning(int(self.host_status[0, 0]) & 0xFFFFFFFF)
         check(L.gsb_render(ctypes.byref(cam), self.P, self.geom.data_ptr(), self.binning.data_ptr(),
-                           self.bin_bytes, R, self.image_buf.data_ptr(), self.color.data_ptr(), st), "gsb_render")
+                           self.bin_bytes, self.cap, self.image_buf.data_ptr(), self.color.data_ptr(),
+                           self.host_status[1].data_ptr(), st), "gsb_render")
         self._keep = (cam, g)
+
+    def _settle(self) -> bool:
+        """Wait for the status words of the last forward's preprocess phase (early in the stream: the GPU still has
+        the rest of the iteration queued, so this never starves it).  Returns True if the binning buffer was big
+        enough; otherwise grows it (the device skipped the optimizer update by itself) and returns False."""
+        self._ev_pre.synchronize()
+        R = int(self.host_status[0, 0]) & 0xFFFFFFFF
+        self.last_R = R
+        if R > self.cap:
+            self.overflows += 1
+            self._size_binning(R)
+            return False
+        if R > 0.85 * self.cap:                              # grow ahead of need
+            self._size_binning(R)
+        return True
+
+    def render(self, view: int) -> torch.Tensor:
+        """Forward only (exact: repeated with a larger buffer in the unlikely case the capacity was exceeded)."""
+        self._launch_forward(view)
+        if not self._settle():
+            self._launch_forward(view)
+            assert self._settle()
         return self.color
 
     def loss_and_backward(self, view: int, gt: torch.Tensor) -> None:
@@ -229,7 +274,7 @@ class JointTrainer:
         self.pose_grad.zero_()
         gr.dL_dpose = self.pose_grad[view].data_ptr()
         check(L.gsb_backward(ctypes.byref(cam), ctypes.byref(g), self.geom.data_ptr(), self.binning.data_ptr(),
-                             self.last_R, self.image_buf.data_ptr(), self.dL_dimg.data_ptr(), ctypes.byref(gr), st),
+                             self.cap, self.image_buf.data_ptr(), self.dL_dimg.data_ptr(), ctypes.byref(gr), st),
               "gsb_backward")
 
     def loss_value(self) -> torch.Tensor:
@@ -240,7 +285,8 @@ class JointTrainer:
     def reduce_grads(self) -> None:
         if self.world_size > 1:
             from .parallel import allreduce_sum_
-            allreduce_sum_((self.grads, self.pose_grad), self.pg)
+            self._pg_buf[-1:].copy_(self._status_t[1:2])
+            allreduce_sum_((self.grads, self._pg_buf), self.pg)
 
     def optimizer_step(self, grad_scale: Optional[float] = None) -> None:
         """PerPointAdam.step over the 6 Gaussian tensors + the pose table in one launch
@@ -264,7 +310,14 @@ class JointTrainer:
             entries.append(dict(param=self.poses, grad=self.pose_grad, exp_avg=self.pose_m, exp_avg_sq=self.pose_v,
                                 per_point_lr=None, row_len=7, step_size=self.cam_sched(self.iteration) * corr,
                                 beta1=b1, beta2=b2, eps=eps, weight_decay=0.0, grad_scale=gs))
-        launch_adam(entries, self.flags)
+        launch_adam(entries, self.flags, skip_ptr=self._skip_ptr())
+
+    def _skip_ptr(self):
+        """Device word that makes the optimizer kernels skip the update: the forward's overflow status
+        (multi-GPU: its sum over ranks, so that every replica takes the same decision)."""
+        if self.world_size > 1:
+            return self._ovf.data_ptr()
+        return self._status_dev + 4
 
     def _lrs(self):
         c = self.cfg
@@ -296,6 +349,7 @@ class JointTrainer:
         # one small SUM all-reduce carries both the gate flags (as counts) and the pose-gradient table
         # (self.pose_grad is a view of self._xch[8:]); it is also the pre-barrier of the fused kernel
         self._xch[:8].copy_(self.flags)
+        self._xch[7:8].copy_(self._status_t[1:2])          # slot 7: binning overflow (summed over ranks)
         dist.all_reduce(self._xch, op=dist.ReduceOp.SUM, group=self.pg)
         self.flags.copy_(self._xch[:8])
         # 2. the fused kernel over this rank's shard
@@ -316,28 +370,70 @@ class JointTrainer:
         check(L.gsb_fused_rs_adam_ag(self.world_size, self.rank, self._peer_grads.ptr_array(),
                                      self._peer_params.ptr_array(), self.exp_avg.data_ptr(),
                                      self.exp_avg_sq.data_ptr(), lo, len(pieces), parr, self.flags.data_ptr(),
-                                     1.0 / self.world_size, st), "gsb_fused_rs_adam_ag")
+                                     self._ovf.data_ptr(), 1.0 / self.world_size, st), "gsb_fused_rs_adam_ag")
         # 3. pose table: replicated Adam on the all-reduced pose gradients
         if c.optim_pose:
             launch_adam([dict(param=self.poses, grad=self.pose_grad, exp_avg=self.pose_m, exp_avg_sq=self.pose_v,
                               per_point_lr=None, row_len=7, step_size=self.cam_sched(self.iteration) * corr,
                               beta1=b1, beta2=b2, eps=eps, weight_decay=0.0, grad_scale=1.0 / self.world_size)],
-                        self._pose_flags)
+                        self._pose_flags, skip_ptr=self._ovf.data_ptr())
         # 4. nobody may start the next forward before every rank's parameter stores have landed
         dist.all_reduce(self._sync, group=self.pg)
 
-    def step(self, view: int, gt: Optional[torch.Tensor] = None) -> None:
-        """One reference iteration on `view` (train.py:140-211)."""
-        self.iteration += 1
-        if gt is None:
-            gt = self.gt[view]
-        self.render(view)
+    def _run_iteration(self, view: int, gt: torch.Tensor, do_opt: bool) -> None:
+        self._launch_forward(view)
         self.loss_and_backward(view, gt)
+        if not do_opt:
+            return
         if self.exchange == "fused_p2p":
             self.fused_exchange_step()
         else:
             self.reduce_grads()
             self.optimizer_step()
+
+    def step(self, view: int, gt: Optional[torch.Tensor] = None) -> None:
+        """One reference iteration on `view` (train.py:140-211): update_learning_rate(iteration), oneupSHdegree every
+        1000 iterations, render, loss, backward, optimizer step (skipped on the very last iteration, :209-211).
+        With G GPUs one call consumes G views (one per rank): `iteration` counts VIEWS, so the learning-rate and
+        SH-degree schedules advance per view as in the reference, while Adam's bias correction counts optimizer
+        steps.  Nothing in here waits for the GPU except `_settle()`, which waits for an event early in the stream."""
+        c = self.cfg
+        before = self.iteration
+        self.iteration += self.world_size
+        if self.iteration // c.sh_increase_interval > before // c.sh_increase_interval:
+            self.active_sh_degree = min(self.active_sh_degree + 1, c.max_sh_degree)     # oneupSHdegree
+        if gt is None:
+            gt = self.gt[view]
+        do_opt = self.iteration < c.iterations
+        self._run_iteration(view, gt, do_opt)
+        if not self._settle():
+            # The binning capacity was exceeded: the device skipped the update by itself (gated on the overflow word,
+            # summed over ranks in multi-GPU mode), so parameters and moments are untouched.  Single GPU: repeat the
+            # iteration with the larger buffer.  Multi GPU: the other ranks cannot know yet -- stop loudly.
+            if self.world_size > 1:
+                raise _lib.GsbError(f"rank {self.rank}: {self.last_R} instances exceeded the binning capacity; the "
+                                    "optimizer update of this step was skipped on every rank (parameters are "
+                                    "consistent).  Raise JointTrainer.headroom.")
+            if do_opt:
+                self.opt_step -= 1
+            self._run_iteration(view, gt, do_opt)
+            assert self._settle()
+
+    def blend_stats(self, view: int, gt: Optional[torch.Tensor] = None) -> Dict[str, int]:
+        """Pair statistics of the blend kernels for one forward+backward of `view` (instrumented re-run of the same
+        kernels, outside any timed region): evaluated / contributing (pixel, Gaussian) pairs."""
+        L = _lib.lib()
+        self.render(view)
+        self.loss_and_backward(view, self.gt[view] if gt is None else gt)
+        cam, _ = self._keep
+        stats = torch.zeros(8, dtype=torch.int64, device=self.dev)
+        check(L.gsb_blend_stats(ctypes.byref(cam), self.P, self.geom.data_ptr(), self.binning.data_ptr(), self.cap,
+                                self.image_buf.data_ptr(), self.color.data_ptr(), self.dL_dimg.data_ptr(),
+                                stats.data_ptr(), _lib.stream_ptr()), "gsb_blend_stats")
+        s = stats.cpu().tolist()
+        return dict(instances=self.last_R, fwd_warp_iters=s[0], fwd_pairs_evaluated=64 * s[0], fwd_pairs_contributing=s[1],
+                    bwd_warp_iters=s[2], bwd_pairs_evaluated=64 * s[2], bwd_pairs_contributing=s[3],
+                    bwd_warp_iters_reduced=s[4])
 
     # ------------------------------------------------------------------------------------------
     def algorithmic_bytes(self) -> Dict[str, float]:

@@ -21,6 +21,11 @@ from instantsplat_b200 import rasterizer as _R
 _live = {}      # geomBuffer.data_ptr() -> state of the forward (the upstream backward signature carries no opacities)
 
 
+def _forget(key, st):
+    if _live.get(key) is st:
+        del _live[key]
+
+
 def _opt(t):
     return t if (t is not None and t.numel() > 0) else None
 
@@ -37,19 +42,23 @@ def rasterize_gaussians(bg, means3D, colors_precomp, opacities, scales, rotation
     M = sh_.shape[1] if sh_ is not None else 1
     color, radii, st = _R._forward(rs, means3D, _opt(scales), _opt(rotations), opacities.reshape(-1), sh_, None, 1, M,
                                    _opt(colors_precomp), _opt(cov3D_precomp), None, 0)
+    _R._verify(st, means3D.device)                   # upstream returns num_rendered as a host int: settle it now
     geom, binning, image = st.geom, st.binning, st.image
     st.geom = st.binning = st.image = None          # the registry must not keep the scratch alive
+    # upstream's signature has no room for a handle, so the call is keyed on the buffer's address; the entry dies
+    # with the tensor (finalizer, only if it still belongs to this call) and a forward whose geomBuffer reuses
+    # the address replaces it
     key = geom.data_ptr()
     _live[key] = st
-    weakref.finalize(geom, _live.pop, key, None)     # forget the call when the caller drops geomBuffer
-    return st.R, color, radii, geom, binning, image
+    weakref.finalize(geom, _forget, key, st)         # forget the call when the caller drops geomBuffer
+    return st.R_true, color, radii, geom, binning, image
 
 
 def rasterize_gaussians_backward(bg, means3D, radii, colors_precomp, scales, rotations, scale_modifier, cov3D_precomp,
                                  viewmatrix, projmatrix, tanfovx, tanfovy, dL_dout_color, sh, degree, campos,
                                  geomBuffer, num_rendered, binningBuffer, imgBuffer, debug):
     st = _live.get(geomBuffer.data_ptr())
-    if st is None or st.R != int(num_rendered):
+    if st is None or st.R_true != int(num_rendered):
         raise RuntimeError("rasterize_gaussians_backward: unknown geomBuffer (call rasterize_gaussians first)")
     st.geom, st.binning, st.image = geomBuffer, binningBuffer, imgBuffer
     try:

@@ -24,7 +24,7 @@ def test_build_and_exports_match_header():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in gsb200.h but not exported"
     assert set(I._lib.EXPORTS) == declared
-    assert L.gsb_abi_version() == 1
+    assert L.gsb_abi_version() == 2
     # sizing helpers are pure host code
     assert L.gsb_geom_bytes(1000) > 1000 * (16 * 3 + 48)
     assert L.gsb_binning_bytes(5000, 1920, 1080) > 5000 * 64

@@ -92,7 +92,7 @@ def check_grads(gc, go, tol=1e-3, names=NAMES + ("pose", "means2D")):
 # ----------------------------------------------------------------------------------------------
 def test_library_loads_and_reports_device():
     import instantsplat_b200 as I
-    assert I.lib().gsb_abi_version() == 1
+    assert I.lib().gsb_abi_version() == 2
     assert torch.cuda.get_device_capability()[0] >= 10, "these kernels are built for sm_100a only"
 
 
@@ -225,8 +225,8 @@ def test_exact_cull_is_lossless():
 
 
 def test_blend_kernel_versions_agree():
-    """v1 (one pixel per lane), v2 (two pixels, packed f32x2) and v3 (four pixels) blend kernels, with and
-    without TMA bulk staging, on a scene whose image size is not a multiple of the tile size."""
+    """v1 (one pixel per lane) and v2 (two pixels, packed f32x2) blend kernels, with and without TMA bulk
+    staging, on a scene whose image size is not a multiple of the tile size."""
     import instantsplat_b200 as I
     L = I.lib()
     sc = surface_scene(40_000, 3, 300, 200, seed=17, sh_degree=2)
@@ -234,7 +234,7 @@ def test_blend_kernel_versions_agree():
     gt = torch.rand(3, sc.height, sc.width, generator=torch.Generator().manual_seed(3))
     res = {}
     try:
-        for ver, bulk in ((1, 0), (2, 1), (2, 0), (3, 1), (3, 0)):
+        for ver, bulk in ((1, 0), (2, 1), (2, 0)):
             assert L.gsb_set_option(b"blend_version", ver) == 0 and L.gsb_set_option(b"stage_bulk", bulk) == 0
             res[(ver, bulk)] = cuda_run(sc, 2, bg, gt)
     finally:
@@ -250,7 +250,7 @@ def test_blend_kernel_versions_agree():
         for k in NAMES + ("pose", "means2D"):
             assert rel_err(b_g[k], a_g[k]) < 5e-3, (key, k)
     # bulk vs cooperative staging of the same version must agree exactly in the forward
-    assert torch.equal(res[(3, 1)][0], res[(3, 0)][0]) and torch.equal(res[(2, 1)][0], res[(2, 0)][0])
+    assert torch.equal(res[(2, 1)][0], res[(2, 0)][0])
 
 
 def test_generic_boundary_b2_nonidentity_view_packed_sh():

@@ -35,7 +35,9 @@ constexpr int kScanT = 1024;
 __global__ void __launch_bounds__(kScanT) k_tile_scan(GeomView gv, int ntiles) {
   __shared__ unsigned long long s_warp[32];
   __shared__ uint32_t s_max[32];
+  __shared__ uint32_t s_nq[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 2) s_nq[tid] = 0u;
   const int per = (ntiles + kScanT - 1) / kScanT;
   const int lo = tid * per, hi = min(ntiles, lo + per);
   unsigned long long sum = 0;
@@ -66,15 +68,21 @@ __global__ void __launch_bounds__(kScanT) k_tile_scan(GeomView gv, int ntiles) {
   __syncthreads();
   unsigned long long run = (inc - sum) + (warp ? s_warp[warp - 1] : 0ull);
   for (int t = lo; t < hi; ++t) {
+    const uint32_t c = gv.tcount[t];
     gv.tstart[t] = (uint32_t)min(run, 0xFFFFFFF0ull);     // saturating: such a tile is beyond any capacity
     gv.tcursor[t] = 0u;
-    run += gv.tcount[t];
+    run += c;
+    if (c > kLargeList) gv.q_huge[atomicAdd(&s_nq[1], 1u)] = (uint32_t)t;        // rare: long lists are queued for
+    else if (c > kSmallList) gv.q_large[atomicAdd(&s_nq[0], 1u)] = (uint32_t)t;  // the persistent sort kernels
   }
+  __syncthreads();
   if (tid == kScanT - 1) {
     gv.status[kStR] = (uint32_t)min(s_warp[31], 0xFFFFFFF0ull);
     gv.status[kStOverflow] = 0u;
     gv.status[kStMaxList] = s_max[0];
     gv.status[kStHugeTiles] = 0u;
+    gv.status[kStNLarge] = s_nq[0];
+    gv.status[kStNHuge] = s_nq[1];
   }
 }
 
@@ -91,15 +99,21 @@ k_scatter(int P, GeomView gv, BinView bv, int W, int H, int gx, int exact_cull, 
   unsigned long long key = 0ull;
   bool coop = false;
   TileSink sink{gv.tcount, gv.tstart, gv.tcursor, bv.pairs, cap};
+  uint32_t mask = 0u;
   if (n) {
-    const float4 a = gv.xyAB[i], b = gv.Codq[i];
     const uint2 rc = gv.rect[i];
-    p.x = a.x; p.y = a.y; p.A = a.z; p.B = a.w; p.C = b.x; p.qthr = b.w;
     p.rx0 = rc.x & 0xFFFF; p.rx1 = rc.x >> 16; p.ry0 = rc.y & 0xFFFF; p.ry1 = rc.y >> 16;
+    const float4 b = gv.Codq[i];
     key = ((unsigned long long)__float_as_uint(b.z) << 32) | (unsigned long long)(uint32_t)i;
     coop = (p.rx1 - p.rx0) * (p.ry1 - p.ry0) > kCoopTiles;
-    if (!coop) visit_tiles(p, W, H, gx, exact_cull != 0, sink, key);
+    if (coop) {
+      const float4 a = gv.xyAB[i];
+      p.x = a.x; p.y = a.y; p.A = a.z; p.B = a.w; p.C = b.x; p.qthr = b.w;
+    } else {
+      mask = gv.kmask[i];        // exactly the tiles k_preprocess counted
+    }
   }
+  warp_sink_masks(mask, p.rx0, p.ry0, p.rx1 - p.rx0, gx, sink, key);
   visit_tiles_coop(coop, p, W, H, gx, exact_cull != 0, sink, key);
 }
 
@@ -136,60 +150,78 @@ __device__ __forceinline__ void cta_bitonic(unsigned long long* a, uint32_t n) {
   }
 }
 
+// Gather the splat records of a sorted id list into the tile's slab.  kGU entries per thread per round with all
+// their 16-byte loads issued before the first store (the loads are scattered L2 hits: latency, not bandwidth).
+constexpr int kGU = 2;
 __device__ __forceinline__ void gather_slab(const GeomView& gv, const BinView& bv, const unsigned long long* sorted,
                                             uint32_t start, uint32_t n, int nthreads) {
-  for (uint32_t j = threadIdx.x; j < n; j += nthreads) {
-    const uint32_t i = (uint32_t)sorted[j];
-    const float4 a = gv.xyAB[i], b = gv.Codq[i], c = gv.rgbr[i];
-    const size_t e = (size_t)start + j;
-    // conic pre-scaled into the log2 domain: power*log2(e) = A' dx^2 + B' dx dy + C' dy^2
-    bv.s0[e] = make_float4(a.x, a.y, -0.5f * kLog2e * a.z, -kLog2e * a.w);
-    bv.s1[e] = make_float4(-0.5f * kLog2e * b.x, b.y, 0.5f * kLog2e * b.w, __uint_as_float(i));
-    bv.s2[e] = make_float4(c.x, c.y, c.z, 0.f);
+  for (uint32_t j0 = threadIdx.x; j0 < n; j0 += kGU * nthreads) {
+    uint32_t id[kGU];
+    float4 a[kGU], b[kGU], c[kGU];
+#pragma unroll
+    for (int u = 0; u < kGU; ++u) {
+      const uint32_t j = j0 + u * nthreads;
+      id[u] = j < n ? (uint32_t)sorted[j] : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int u = 0; u < kGU; ++u)
+      if (id[u] != 0xFFFFFFFFu) { a[u] = gv.xyAB[id[u]]; b[u] = gv.Codq[id[u]]; c[u] = gv.rgbr[id[u]]; }
+#pragma unroll
+    for (int u = 0; u < kGU; ++u)
+      if (id[u] != 0xFFFFFFFFu) {
+        const size_t e = (size_t)start + j0 + u * nthreads;
+        // conic pre-scaled into the log2 domain: power*log2(e) = A' dx^2 + B' dx dy + C' dy^2
+        bv.s0[e] = make_float4(a[u].x, a[u].y, -0.5f * kLog2e * a[u].z, -kLog2e * a[u].w);
+        bv.s1[e] = make_float4(-0.5f * kLog2e * b[u].x, b[u].y, 0.5f * kLog2e * b[u].w, __uint_as_float(id[u]));
+        bv.s2[e] = make_float4(c[u].x, c[u].y, c[u].z, 0.f);
+      }
   }
 }
 
 constexpr uint32_t kSkew = 24;     // a bucket longer than this sends the tile to the bitonic fallback
 
-// NT threads, KPT keys per thread: handles lists of n_lo <= n <= n_hi <= NT*KPT entries (other tiles return at
-// once, so several size classes can be launched over the same grid).  HUGE: any n, sorted in global memory.
+// Sorts one tile's segment and gathers its slab.  NT threads, KPT keys per thread (lists of up to NT*KPT entries);
+// HUGE: any length, sorted in global memory.
+//
+// Shared-memory sort: one bucket pass over the tile's own depth range -- bucket(d) = floor((d - dmin) * CAP /
+// (dmax - dmin + 1)), monotone in the depth bits, CAP buckets for <= CAP keys -- then each thread finishes its KPT
+// consecutive buckets with an insertion sort on the full 64-bit (depth, id) key.  Keys are re-read from global
+// memory (L1/L2 hits) in the three passes instead of being held in registers: occupancy matters more here than
+// load instructions, the kernel is barrier/latency bound.
 template <int NT, int KPT, bool HUGE>
-__global__ void __launch_bounds__(NT)
-k_tile_sort(GeomView gv, BinView bv, uint32_t cap, uint32_t n_lo, uint32_t n_hi) {
+__device__ __forceinline__ void tile_sort_one(const GeomView& gv, const BinView& bv, uint32_t cap, uint32_t tile,
+                                              unsigned char* smraw) {
   constexpr int CAP = NT * KPT;
-  extern __shared__ __align__(16) unsigned char smraw[];
+  constexpr int NW = NT / 32;
   unsigned long long* sorted = reinterpret_cast<unsigned long long*>(smraw);   // [CAP]
   uint32_t* hist = reinterpret_cast<uint32_t*>(smraw + (size_t)CAP * 8);       // [CAP] buckets
-  __shared__ uint32_t s_w[32], s_w2[32];
-  __shared__ unsigned long long s_mul;
-  __shared__ uint32_t s_dmin;
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_dmin, s_dmax;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile = blockIdx.x;
   const uint32_t start = gv.tstart[tile], cnt = gv.tcount[tile], cur = gv.tcursor[tile];
   const uint32_t avail = start < cap ? cap - start : 0u;
   const uint32_t n = min(min(cnt, cur), avail);
-  if (n < n_lo || n > n_hi) return;
   if (tid == 0) {
     const uint32_t s = min(start, cap);
     bv.ranges[tile] = make_uint2(s, s + n);
     if (cnt > avail) atomicOr(gv.status + kStOverflow, 1u);
     if (HUGE) atomicAdd(gv.status + kStHugeTiles, 1u);
+    s_dmin = 0xFFFFFFFFu; s_dmax = 0u;
   }
   if (n == 0) return;
+  const unsigned long long* seg = bv.pairs + start;
   if (HUGE) {
-    unsigned long long* seg = bv.pairs + start;
-    cta_bitonic<NT>(seg, n);
+    cta_bitonic<NT>(const_cast<unsigned long long*>(seg), n);
     gather_slab(gv, bv, seg, start, n, NT);
     return;
   }
-  // ---- load keys, depth range
-  unsigned long long k[KPT];
+  __syncthreads();
+  // ---- pass 1: depth range (and clear the buckets)
   uint32_t dmin = 0xFFFFFFFFu, dmax = 0u;
 #pragma unroll
   for (int j = 0; j < KPT; ++j) {
     const uint32_t idx = (uint32_t)(j * NT + tid);
-    k[j] = idx < n ? bv.pairs[(size_t)start + idx] : ~0ull;
-    if (idx < n) { const uint32_t d = (uint32_t)(k[j] >> 32); dmin = min(dmin, d); dmax = max(dmax, d); }
+    if (idx < n) { const uint32_t d = (uint32_t)(__ldg(seg + idx) >> 32); dmin = min(dmin, d); dmax = max(dmax, d); }
     hist[idx] = 0u;
   }
 #pragma unroll
@@ -197,32 +229,19 @@ k_tile_sort(GeomView gv, BinView bv, uint32_t cap, uint32_t n_lo, uint32_t n_hi)
     dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
     dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
   }
-  if (lane == 0) { s_w[warp] = dmin; s_w2[warp] = dmax; }
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t a = lane < NT / 32 ? s_w[lane] : 0xFFFFFFFFu, b = lane < NT / 32 ? s_w2[lane] : 0u;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
-      b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
-    }
-    if (lane == 0) {
-      s_dmin = a;
-      // bucket(d) = ((d - dmin) * mul) >> 32 is monotone in d and < CAP
-      s_mul = ((unsigned long long)CAP << 32) / ((unsigned long long)(b - a) + 1ull);
-    }
-  }
+  if (lane == 0) { atomicMin(&s_dmin, dmin); atomicMax(&s_dmax, dmax); }
   __syncthreads();
   dmin = s_dmin;
-  const unsigned long long mul = s_mul;
-  uint32_t bkt[KPT];
+  // float arithmetic is monotone (conversion, multiplication by a positive constant and truncation all are), which
+  // is all the bucket function has to be; the clamp covers rounding at the top end
+  const float scale = (float)CAP / ((float)(s_dmax - dmin) + 1.0f);
+  // ---- pass 2: histogram
 #pragma unroll
   for (int j = 0; j < KPT; ++j) {
     const uint32_t idx = (uint32_t)(j * NT + tid);
-    bkt[j] = 0u;
     if (idx < n) {
-      bkt[j] = (uint32_t)(((unsigned long long)((uint32_t)(k[j] >> 32) - dmin) * mul) >> 32);
-      atomicAdd(hist + bkt[j], 1u);
+      const uint32_t d = (uint32_t)(__ldg(seg + idx) >> 32);
+      atomicAdd(hist + min((uint32_t)(CAP - 1), (uint32_t)((float)(d - dmin) * scale)), 1u);
     }
   }
   __syncthreads();
@@ -238,26 +257,22 @@ k_tile_sort(GeomView gv, BinView bv, uint32_t cap, uint32_t n_lo, uint32_t n_hi)
   }
   if (lane == 31) s_w[warp] = inc;
   const bool skew = __syncthreads_or(big > kSkew) != 0;
-  if (warp == 0) {
-    uint32_t w = lane < NT / 32 ? s_w[lane] : 0u;
+  uint32_t run = inc - sum;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += v;
-    }
-    s_w[lane] = w;
-  }
-  __syncthreads();
-  uint32_t run = (inc - sum) + (warp ? s_w[warp - 1] : 0u);
+  for (int w = 0; w < NW; ++w) run += (w < warp) ? s_w[w] : 0u;
   const uint32_t my_begin = run;
 #pragma unroll
   for (int j = 0; j < KPT; ++j) { hist[tid * KPT + j] = run; run += c[j]; }
   __syncthreads();
-  // ---- scatter into buckets (order inside a bucket is arbitrary here)
+  // ---- pass 3: scatter into buckets (order inside a bucket is arbitrary here)
 #pragma unroll
   for (int j = 0; j < KPT; ++j) {
     const uint32_t idx = (uint32_t)(j * NT + tid);
-    if (idx < n) sorted[atomicAdd(hist + bkt[j], 1u)] = k[j];
+    if (idx < n) {
+      const unsigned long long k = __ldg(seg + idx);
+      const uint32_t d = (uint32_t)(k >> 32);
+      sorted[atomicAdd(hist + min((uint32_t)(CAP - 1), (uint32_t)((float)(d - dmin) * scale)), 1u)] = k;
+    }
   }
   __syncthreads();
   if (skew) {
@@ -281,10 +296,33 @@ k_tile_sort(GeomView gv, BinView bv, uint32_t cap, uint32_t n_lo, uint32_t n_hi)
   gather_slab(gv, bv, sorted, start, n, NT);
 }
 
+// ---- kernels ------------------------------------------------------------------------------------------------
 constexpr int kSmallNT = 256, kSmallKPT = 8;     // lists of up to 2048 entries: 24 KB shared memory
 constexpr int kLargeNT = 512, kLargeKPT = 16;    // up to 8192 entries: 96 KB shared memory
-constexpr uint32_t kSmallCap = kSmallNT * kSmallKPT, kLargeCap = kLargeNT * kLargeKPT;
-constexpr size_t kSmallSmem = (size_t)kSmallCap * 12, kLargeSmem = (size_t)kLargeCap * 12;
+static_assert(kSmallNT * kSmallKPT == (int)kSmallList && kLargeNT * kLargeKPT == (int)kLargeList, "size classes");
+constexpr size_t kSmallSmem = (size_t)kSmallList * 12, kLargeSmem = (size_t)kLargeList * 12;
+constexpr int kQueueCtas = 148;                  // persistent CTAs draining the long-list queues (one per SM)
+
+// one CTA per tile; tiles with longer lists were queued by k_tile_scan and are skipped here
+__global__ void __launch_bounds__(kSmallNT, 5) k_tile_sort(GeomView gv, BinView bv, uint32_t cap) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  if (gv.tcount[blockIdx.x] > kSmallList) return;
+  tile_sort_one<kSmallNT, kSmallKPT, false>(gv, bv, cap, blockIdx.x, smraw);
+}
+
+// persistent: CTA b takes queue entries b, b + grid, ...  (normally the queues are empty and this is a no-op)
+__global__ void __launch_bounds__(kLargeNT) k_tile_sort_long(GeomView gv, BinView bv, uint32_t cap) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const uint32_t nl = gv.status[kStNLarge], nh = gv.status[kStNHuge];
+  for (uint32_t q = blockIdx.x; q < nl; q += gridDim.x) {
+    tile_sort_one<kLargeNT, kLargeKPT, false>(gv, bv, cap, gv.q_large[q], smraw);
+    __syncthreads();
+  }
+  for (uint32_t q = blockIdx.x; q < nh; q += gridDim.x) {
+    tile_sort_one<kLargeNT, 1, true>(gv, bv, cap, gv.q_huge[q], smraw);
+    __syncthreads();
+  }
+}
 
 }  // namespace
 
@@ -299,10 +337,9 @@ int gsb_launch_binning(int P, const GeomView& gv, const BinView& bv, int W, int 
   static bool attr_set[64] = {};
   int dev = 0;
   GSB_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    GSB_CUDA(cudaFuncSetAttribute(k_tile_sort<kLargeNT, kLargeKPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kLargeSmem));
-    attr_set[dev] = true;
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    GSB_CUDA(cudaFuncSetAttribute(k_tile_sort_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLargeSmem));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int gx = (W + kBlock - 1) / kBlock, gy = (H + kBlock - 1) / kBlock;
   if (P > 0) {
@@ -310,10 +347,9 @@ int gsb_launch_binning(int P, const GeomView& gv, const BinView& bv, int W, int 
     k_scatter<<<(P + kThreads - 1) / kThreads, kThreads, 0, st>>>(P, gv, bv, W, H, gx, exact_cull, cap);
   }
   {
-    ProfScope ps(GSB_K_SORT_TILE, st, 3);
-    k_tile_sort<kSmallNT, kSmallKPT, false><<<gx * gy, kSmallNT, kSmallSmem, st>>>(gv, bv, cap, 0u, kSmallCap);
-    k_tile_sort<kLargeNT, kLargeKPT, false><<<gx * gy, kLargeNT, kLargeSmem, st>>>(gv, bv, cap, kSmallCap + 1, kLargeCap);
-    k_tile_sort<kLargeNT, 1, true><<<gx * gy, kLargeNT, 0, st>>>(gv, bv, cap, kLargeCap + 1, 0xFFFFFFFFu);
+    ProfScope ps(GSB_K_SORT_TILE, st, 2);
+    k_tile_sort<<<gx * gy, kSmallNT, kSmallSmem, st>>>(gv, bv, cap);
+    k_tile_sort_long<<<kQueueCtas, kLargeNT, kLargeSmem, st>>>(gv, bv, cap);
   }
   GSB_CUDA(cudaGetLastError());
   return GSB_OK;

@@ -52,7 +52,10 @@ constexpr int kPT = 128;           // threads (= Gaussians) per CTA in the per-G
 constexpr int kMaxTiles = 65536;   // tile ids are 16 bit (a 4K frame has 32400 tiles)
 
 // status words written by the forward (device) and copied to the caller's pinned host array
-enum { kStR = 0, kStOverflow = 1, kStMaxList = 2, kStHugeTiles = 3, kStWords = 8 };
+enum { kStR = 0, kStOverflow = 1, kStMaxList = 2, kStHugeTiles = 3, kStNLarge = 4, kStNHuge = 5, kStWords = 8 };
+// tile-list size classes of the per-tile sort (gs_bin.cu): <= kSmallList entries are sorted by the one-CTA-per-tile
+// kernel; longer lists are queued by k_tile_scan and drained by two persistent kernels
+constexpr uint32_t kSmallList = 2048, kLargeList = 8192;
 
 // ---- geom: P-sized scratch + per-tile counters (caller-owned, gsb_geom_bytes) -------------
 struct GeomView {
@@ -62,6 +65,7 @@ struct GeomView {
   float4* rgbr;        // r, g, b, radius
   uint2* rect;         // x: rx0 | rx1<<16   y: ry0 | ry1<<16
   uint32_t* tiles;     // tile instances per Gaussian (after culling)
+  uint32_t* kmask;     // keep mask over the tile rect (rects of <= kCoopTiles tiles)
   uint8_t* clamped;
   float4* dacc;        // [3P] backward accumulators
   float* pose_part;    // [nblocks*16]
@@ -70,6 +74,8 @@ struct GeomView {
   uint32_t* tcount;    // [kMaxTiles] instances per tile (counted by k_preprocess)
   uint32_t* tstart;    // [kMaxTiles] exclusive scan of tcount
   uint32_t* tcursor;   // [kMaxTiles] emission cursors (k_scatter)
+  uint32_t* q_large;   // [kMaxTiles] tiles whose list has kSmallList < n <= kLargeList entries
+  uint32_t* q_huge;    // [kMaxTiles] tiles with longer lists
   size_t total;
 };
 
@@ -85,6 +91,7 @@ static inline GeomView geom_view(void* base, int P) {
   v.rgbr = (float4*)take(Pp * 16);
   v.rect = (uint2*)take(Pp * 8);
   v.tiles = (uint32_t*)take(Pp * 4);
+  v.kmask = (uint32_t*)take(Pp * 4);
   v.clamped = (uint8_t*)take(Pp);
   v.dacc = (float4*)take(Pp * 48);
   size_t nb = (Pp + kPT - 1) / kPT;
@@ -94,6 +101,8 @@ static inline GeomView geom_view(void* base, int P) {
   v.tcount = (uint32_t*)take((size_t)kMaxTiles * 4);
   v.tstart = (uint32_t*)take((size_t)kMaxTiles * 4);
   v.tcursor = (uint32_t*)take((size_t)kMaxTiles * 4);
+  v.q_large = (uint32_t*)take((size_t)kMaxTiles * 4);
+  v.q_huge = (uint32_t*)take((size_t)kMaxTiles * 4);
   v.total = off;
   return v;
 }

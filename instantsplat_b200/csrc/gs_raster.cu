@@ -346,7 +346,7 @@ k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
   project_geometry(*cam, g, in.cov3D ? in.cov3D + (size_t)6 * i : nullptr, p);
   if (!active) p.visible = 0;
   float qthr = -1.f;
-  uint32_t ntiles = 0;
+  uint32_t ntiles = 0, kmask = 0u;
   bool coop = false;
   SplatRect sr_;
   sr_.x = sr_.y = sr_.A = sr_.B = sr_.C = 0.f; sr_.qthr = -1.f;
@@ -366,7 +366,12 @@ k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
     const int area = (p.rx1 - p.rx0) * (p.ry1 - p.ry0);
     if (cull && qthr < 0.f) ntiles = 0;
     else if (area > kCoopTiles) coop = true;
-    else ntiles = visit_tiles(sr_, cam->W, cam->H, cam->gx, cull, sink, 0ull);
+    else {
+      // per-tile counts: plain fire-and-forget RED.ADD per kept tile (measured faster here than warp-aggregating
+      // them: nothing waits for the result, unlike the emit pass in k_scatter)
+      kmask = rect_keep_mask_count(sr_, cam->W, cam->H, cam->gx, cull, gv.tcount);
+      ntiles = (uint32_t)__popc(kmask);
+    }
   } else {
     p.x = p.y = p.A = p.B = p.C = 0.f; p.rgb[0] = p.rgb[1] = p.rgb[2] = 0.f;
   }
@@ -380,6 +385,7 @@ k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
   gv.rgbr[i] = make_float4(p.rgb[0], p.rgb[1], p.rgb[2], (float)p.radius);
   gv.rect[i] = make_uint2((uint32_t)p.rx0 | ((uint32_t)p.rx1 << 16), (uint32_t)p.ry0 | ((uint32_t)p.ry1 << 16));
   gv.tiles[i] = ntiles;
+  gv.kmask[i] = kmask;
   gv.clamped[i] = (uint8_t)p.clamped;
   radii[i] = p.radius;
 }

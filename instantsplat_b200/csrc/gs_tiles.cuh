@@ -3,10 +3,12 @@
 // Coverage = the reference's tile rect minus the tiles that the lossless cull
 // (gs_math.cuh rect_may_contribute) proves cannot reach alpha >= 1/255.
 //
-// The emit side never trusts the two evaluations to agree bit for bit: an instance is written only while the
-// tile's cursor is below the counted length (and below the buffer capacity), and the consumer uses
-// min(count, cursor) as the list length.  A borderline tile that flips between the two passes carries no
-// visible contribution by construction of the cull margin, so dropping / missing it does not change the image.
+// Small rects (<= kCoopTiles tiles): k_preprocess stores the keep MASK, and k_scatter replays exactly those tiles.
+// Large rects are re-walked by the whole warp in both passes; there the emit side does not trust the two
+// evaluations to agree bit for bit: an instance is written only while the tile's cursor is below the counted
+// length (and below the buffer capacity), and the consumer uses min(count, cursor) as the list length.  A
+// borderline tile that flips between the two passes carries no visible contribution by construction of the cull
+// margin, so dropping / missing it does not change the image.
 #pragma once
 #include "gs_math.cuh"
 
@@ -48,17 +50,66 @@ __device__ __forceinline__ bool tile_kept(const SplatRect& p, int tx, int ty, in
   return rect_may_contribute(p.x, p.y, p.A, p.B, p.C, p.qthr, x0, y0, x1, y1);
 }
 
-// one thread walks its own (small) rect; returns the number of kept tiles
-__device__ __forceinline__ uint32_t visit_tiles(const SplatRect& p, int W, int H, int gx, bool cull,
-                                                const TileSink& s, unsigned long long key) {
-  uint32_t n = 0;
+// Small rects (area <= kCoopTiles <= 32): bit k of the keep mask = tile (ry0 + k / w, rx0 + k % w) survives the cull.
+// Computed once by k_preprocess and stored, so the emit pass replays exactly the tiles that were counted.
+__device__ __forceinline__ uint32_t rect_keep_mask(const SplatRect& p, int W, int H, bool cull) {
+  uint32_t m = 0u, bit = 1u;
   for (int ty = p.ry0; ty < p.ry1; ++ty)
-    for (int tx = p.rx0; tx < p.rx1; ++tx)
-      if (tile_kept(p, tx, ty, W, H, cull)) {
-        sink_tile(s, (uint32_t)(ty * gx + tx), key);
-        ++n;
+    for (int tx = p.rx0; tx < p.rx1; ++tx) {
+      if (tile_kept(p, tx, ty, W, H, cull)) m |= bit;
+      bit <<= 1;
+    }
+  return m;
+}
+
+// Same walk, also counting every kept tile into tcount (RED.ADD, no return value).
+__device__ __forceinline__ uint32_t rect_keep_mask_count(const SplatRect& p, int W, int H, int gx, bool cull,
+                                                         uint32_t* tcount) {
+  uint32_t m = 0u, bit = 1u;
+  for (int ty = p.ry0; ty < p.ry1; ++ty)
+    for (int tx = p.rx0; tx < p.rx1; ++tx) {
+      if (tile_kept(p, tx, ty, W, H, cull)) { m |= bit; atomicAdd(tcount + (uint32_t)(ty * gx + tx), 1u); }
+      bit <<= 1;
+    }
+  return m;
+}
+
+// Warp-synchronous delivery of every lane's kept tiles (all 32 lanes must call).  Each round every lane offers
+// its next kept tile; lanes offering the SAME tile are merged with match.any so that one atomic per distinct
+// tile is issued (neighbouring Gaussians overlap the same tiles, which otherwise serialises in the L2 atomic
+// unit).  Emit mode: the group leader reserves cnt slots with one atomicAdd and every member takes base + rank.
+__device__ __forceinline__ void warp_sink_masks(uint32_t mask, int rx0, int ry0, int w, int gx, const TileSink& s,
+                                                unsigned long long key) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t inv_w = w > 0 ? (65536u + (uint32_t)w - 1u) / (uint32_t)w : 0u;   // k / w for k < 32, w <= 32
+  while (__any_sync(full, mask != 0u)) {
+    const bool has = mask != 0u;
+    uint32_t tile = 0xFFFFFFFFu;
+    if (has) {
+      const uint32_t k = (uint32_t)__ffs(mask) - 1u;
+      mask &= mask - 1u;
+      const uint32_t ky = (k * inv_w) >> 16;
+      tile = (uint32_t)(ry0 + (int)ky) * (uint32_t)gx + (uint32_t)(rx0 + (int)(k - ky * (uint32_t)w));
+    }
+    const unsigned grp = __match_any_sync(full, tile);
+    const int leader = __ffs(grp) - 1;
+    const uint32_t cnt = (uint32_t)__popc(grp);
+    if (s.pairs) {
+      uint32_t base = 0u;
+      if (has && lane == leader) base = atomicAdd(s.tcursor + tile, cnt);
+      base = __shfl_sync(full, base, leader);
+      if (has) {
+        const uint32_t pos = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+        if (pos < s.tcount[tile]) {
+          const uint32_t dst = s.tstart[tile] + pos;
+          if (dst < s.cap) s.pairs[dst] = key;
+        }
       }
-  return n;
+    } else if (has && lane == leader) {
+      atomicAdd(s.tcount + tile, cnt);
+    }
+  }
 }
 
 // Gaussians whose rect spans more than kCoopTiles tiles are walked by the WHOLE WARP (one tile per lane per

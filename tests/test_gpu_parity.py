@@ -2,9 +2,8 @@
 Python boundary, against the CPU oracle on the same seeded inputs.
 
 Tolerances (BASELINE.json north_star): render <= 1e-4 max abs per pixel; gradients <= 1e-3 relative
-(max |a-b| / max |b| per tensor).  Pixels the oracle flags as *ambiguous* (a pair within fp32
-rounding of the alpha >= 1/255 / T < 1e-4 / power > 0 decision thresholds -- SURVEY.md section 7 hard
-parts) may flip between implementations; they are excluded and counted.
+(max |a-b| / max |b| per tensor) -- held for every case, see tests/_parity.py for the protocol (oracle-flagged
+threshold-ambiguous pixels are counted, bounded, and given zero loss weight in BOTH arms).
 """
 import math
 import os
@@ -15,26 +14,10 @@ import torch
 
 from oracle import gs_oracle as O
 from instantsplat_b200.scenes import make_config, random_scene, surface_scene
+from _parity import (DEV, GRAD_TOL, NAMES, REPORT, assert_image, compare_fused, image_stats, rel_err,
+                     settings_for)
 
 pytestmark = pytest.mark.gpu
-DEV = "cuda"
-NAMES = ("xyz", "rotation", "scaling", "opacity", "f_dc", "f_rest")
-
-
-def rel_err(a, b):
-    a, b = a.detach().cpu().double().reshape(-1), b.detach().cpu().double().reshape(-1)
-    return float((a - b).abs().max() / (b.abs().max() + 1e-20))
-
-
-def settings_for(sc, deg, bg, debug=False):
-    import instantsplat_b200 as I
-    from instantsplat_b200.camera import projection_matrix
-    return I.GaussianRasterizationSettings(
-        image_height=sc.height, image_width=sc.width, tanfovx=math.tan(sc.fovx * 0.5),
-        tanfovy=math.tan(sc.fovy * 0.5), bg=bg.to(DEV), scale_modifier=1.0,
-        viewmatrix=torch.eye(4, device=DEV),
-        projmatrix=projection_matrix(0.01, 100.0, sc.fovx, sc.fovy).t().contiguous().to(DEV),
-        sh_degree=deg, campos=torch.zeros(3, device=DEV), prefiltered=False, debug=debug)
 
 
 def oracle_run(sc, deg, bg, gt, pose=None):
@@ -72,21 +55,15 @@ def cuda_run(sc, deg, bg, gt, fused_loss=True):
     return img.detach(), radii, loss.detach(), grads
 
 
-def check_image(img_cuda, img_or, amb, tol=1e-4):
-    err = (img_cuda.cpu() - img_or).abs().max(0)[0]
-    bad = err > tol
-    n_bad, n_unexplained = int(bad.sum()), int((bad & ~amb).sum())
-    assert n_unexplained == 0, f"{n_unexplained} pixels over {tol} not explained by threshold ambiguity " \
-                               f"(max err {float(err.max()):.3e}, {n_bad} over tol in total)"
-    assert n_bad <= max(8, 1e-3 * err.numel()), f"too many ambiguous flips: {n_bad}"
-    return n_bad
+def check_image(img_cuda, img_or, amb):
+    st = image_stats(img_cuda, img_or, amb)
+    assert_image(st)
+    return st["n_over_tol"]
 
 
-def check_grads(gc, go, tol=1e-3, names=NAMES + ("pose", "means2D")):
-    errs = {k: rel_err(gc[k], go[k]) for k in names}
-    bad = {k: v for k, v in errs.items() if not v < tol}
-    assert not bad, f"gradient relative errors over {tol}: {bad}  (all: {errs})"
-    return errs
+def masked_weights(shape, amb, seed):
+    """Seeded random loss weights, zero on the oracle-flagged (threshold-ambiguous) pixels."""
+    return torch.rand(*shape, generator=torch.Generator().manual_seed(seed)) * (~amb)[None]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -101,109 +78,108 @@ def test_tiny_scene_vs_oracle(deg):
     sc = random_scene(600, 80, 56, seed=21 + deg, sh_degree=deg)      # W,H not multiples of 16
     bg = torch.tensor([0.2, 0.4, 0.1])
     gt = torch.rand(3, sc.height, sc.width, generator=torch.Generator().manual_seed(5))
-    img_o, radii_o, aux, loss_o, g_o = oracle_run(sc, deg, bg, gt)
-    img_c, radii_c, loss_c, g_c = cuda_run(sc, deg, bg, gt)
-    assert (radii_c.cpu() != radii_o).float().mean() < 5e-3
-    check_image(img_c, img_o, aux["ambiguous"])
-    assert abs(float(loss_c) - float(loss_o)) < 2e-5
-    if int(aux["ambiguous"].sum()) == 0:
-        check_grads(g_c, g_o)
-    else:
-        check_grads(g_c, g_o, tol=2e-2)
+    compare_fused(f"tiny600_80x56_deg{deg}", sc, 0, deg, bg, gt=gt)
 
 
 def test_golden_raster_tiny(golden_dir):
     """Committed fp64 oracle output (regression pin; the reference ships no rasterizer vectors)."""
-    import instantsplat_b200 as I
     z = np.load(os.path.join(golden_dir, "raster_tiny.npz"))
     sc = random_scene(400, int(z["width"]), int(z["height"]), seed=77)
     for k in NAMES:
         assert np.array_equal(sc.params[k].numpy(), z["in_" + k])
     bg, gt = torch.from_numpy(z["bg"]), torch.from_numpy(z["gt"])
     img_c, radii_c, loss_c, g_c = cuda_run(sc, 3, bg, gt)
-    check_image(img_c, torch.from_numpy(z["image"]).float(), torch.from_numpy(z["ambiguous"]))
+    n_flip = check_image(img_c, torch.from_numpy(z["image"]).float(), torch.from_numpy(z["ambiguous"]))
     assert abs(float(loss_c) - float(z["loss"])) < 2e-5
-    g_o = {k: torch.from_numpy(z["g_" + k]) for k in NAMES}
-    g_o["pose"], g_o["means2D"] = torch.from_numpy(z["g_pose"]), torch.from_numpy(z["g_means2D"])
-    check_grads(g_c, g_o, tol=2e-3)
+    if n_flip == 0:      # the stored gradients are those of the full training loss (no per-pixel weights to mask)
+        g_o = {k: torch.from_numpy(z["g_" + k]) for k in NAMES}
+        g_o["pose"], g_o["means2D"] = torch.from_numpy(z["g_pose"]), torch.from_numpy(z["g_means2D"])
+        errs = {k: rel_err(g_c[k], g_o[k]) for k in g_o}
+        assert max(errs.values()) < GRAD_TOL, errs
 
 
 def test_config0_10k_random_256():
     """BASELINE.json configs[0]: 10k random Gaussians, one 256x256 camera (the CPU-runnable case)."""
     sc = make_config(0)
-    bg = torch.zeros(3)
     gt = torch.rand(3, 256, 256, generator=torch.Generator().manual_seed(9))
-    img_o, radii_o, aux, loss_o, g_o = oracle_run(sc, 3, bg, gt)
-    img_c, radii_c, loss_c, g_c = cuda_run(sc, 3, bg, gt)
-    n_flip = check_image(img_c, img_o, aux["ambiguous"])
-    assert (radii_c.cpu() != radii_o).float().mean() < 2e-3
-    assert abs(float(loss_c) - float(loss_o)) < 2e-5
-    check_grads(g_c, g_o, tol=1e-3 if n_flip == 0 else 1e-2)
+    compare_fused("configs[0] 10k random 256x256", sc, 0, 3, torch.zeros(3), gt=gt)
 
 
 def test_config1_surface_scene_scaled():
-    """configs[1] shape (surface scene, 3 views, SH deg 0) at 1/10 scale so the oracle finishes in seconds."""
+    """configs[1] shape (surface scene, 3 views, SH deg 0) at 1/10 scale, full frame, training-loss weights."""
     sc = surface_scene(20_000, 3, 160, 160, seed=1001, sh_degree=0)
-    bg = torch.zeros(3)
     gt = torch.rand(3, 160, 160, generator=torch.Generator().manual_seed(4))
     for v in (0, 2):
-        sc1 = surface_scene(20_000, 3, 160, 160, seed=1001, sh_degree=0)
-        sc1.poses = sc.poses[v:v + 1].clone()
-        img_o, radii_o, aux, loss_o, g_o = oracle_run(sc1, 0, bg, gt)
-        img_c, radii_c, loss_c, g_c = cuda_run(sc1, 0, bg, gt)
-        n_flip = check_image(img_c, img_o, aux["ambiguous"])
-        check_grads(g_c, g_o, tol=1e-3 if n_flip == 0 else 1e-2,
-                    names=("xyz", "rotation", "scaling", "opacity", "f_dc", "pose", "means2D"))
-        assert float(g_c["f_rest"].abs().max()) == 0.0
+        compare_fused(f"configs[1]/10 20k 160x160 view {v}", sc, v, 0, torch.zeros(3), gt=gt)
 
 
-def _tile_subset_parity(sc, view, deg, tiles, tol_grad=2e-3):
-    """Full-size scene: the oracle blends only `tiles`; the loss weights are zero elsewhere, so image AND
-    gradients of the two implementations are comparable although the oracle never renders the full frame."""
-    import instantsplat_b200 as I
-    gx = (sc.width + 15) // 16
-    mask = torch.zeros(sc.height, sc.width)
-    for t in tiles:
-        ty, tx = divmod(t, gx)
-        mask[ty * 16:(ty + 1) * 16, tx * 16:(tx + 1) * 16] = 1.0
-    wgt = torch.rand(3, sc.height, sc.width, generator=torch.Generator().manual_seed(11)) * mask
-    cam = O.Camera.instantsplat(sc.width, sc.height, sc.fovx, sc.fovy, sh_degree=deg)
-    po = {k: v.clone().requires_grad_(True) for k, v in sc.params.items()}
-    pose_o = sc.poses[view].clone().requires_grad_(True)
-    img_o, radii_o, aux = O.render_instantsplat(po["xyz"], po["rotation"], po["scaling"], po["opacity"], po["f_dc"],
-                                                po["f_rest"], pose_o, cam, tiles=tiles, return_aux=True)
-    (img_o * wgt).sum().backward()
-    pc = {k: v.to(DEV).clone().requires_grad_(True) for k, v in sc.params.items()}
-    pose_c = sc.poses[view].to(DEV).clone().requires_grad_(True)
-    img_c, radii_c = I.rasterize_fused(pc["xyz"], pc["rotation"], pc["scaling"], pc["opacity"], pc["f_dc"],
-                                       pc["f_rest"], pose_c, torch.zeros(sc.P, 3, device=DEV),
-                                       settings_for(sc, deg, torch.zeros(3)))
-    (img_c * wgt.to(DEV)).sum().backward()
-    m3 = mask.bool()
-    err = ((img_c.detach().cpu() - img_o.detach()).abs().max(0)[0]) * mask
-    bad = (err > 1e-4)
-    assert int((bad & ~aux["ambiguous"]).sum()) == 0, float(err.max())
-    assert int(bad.sum()) <= max(4, 2e-3 * float(mask.sum()))
-    assert (radii_c.cpu() != radii_o).float().mean() < 2e-3
-    tol = tol_grad if int(bad.sum()) == 0 else 2e-2
-    names = ["xyz", "rotation", "scaling", "opacity", "f_dc"] + (["f_rest"] if deg > 0 else [])
-    for k in names:
-        assert rel_err(pc[k].grad, po[k].grad) < tol, (k, rel_err(pc[k].grad, po[k].grad))
-    assert rel_err(pose_c.grad, pose_o.grad) < tol
+def stratified_tiles(gx, gy, n_interior, seed, extra=()):
+    """Corner tiles, one tile per image edge, `n_interior` seeded random interior tiles and `extra`."""
+    g = torch.Generator().manual_seed(seed)
+    tiles = {0, gx - 1, (gy - 1) * gx, gy * gx - 1, gx // 2, (gy - 1) * gx + gx // 3, (gy // 2) * gx, (gy // 3) * gx + gx - 1}
+    while len(tiles) < 8 + n_interior:
+        tx = int(torch.randint(1, gx - 1, (1,), generator=g))
+        ty = int(torch.randint(1, gy - 1, (1,), generator=g))
+        tiles.add(ty * gx + tx)
+    tiles.update(int(t) for t in extra)
+    return sorted(tiles)
+
+
+def enlarge_some(sc, n, factor, seed):
+    """Blow up n seeded Gaussians so that their tile rects exceed the cooperative-emission threshold (> 24 tiles)."""
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randperm(sc.P, generator=g)[:n]
+    sc.params["scaling"][idx] += math.log(factor)
+    return idx
+
+
+def tiles_under(sc, view, deg, idx):
+    """Tile ids under the centres of Gaussians `idx` in `view` (oracle projection, no grad)."""
+    with torch.no_grad():
+        cam = O.Camera.instantsplat(sc.width, sc.height, sc.fovx, sc.fovy, sh_degree=deg)
+        means, rots = O.pose_pretransform(sc.params["xyz"][idx], sc.params["rotation"][idx], sc.poses[view])
+        shs = torch.cat([sc.params["f_dc"][idx], sc.params["f_rest"][idx]], dim=1)
+        pr = O.project(means, torch.exp(sc.params["scaling"][idx]), rots, torch.sigmoid(sc.params["opacity"][idx]), shs, cam)
+    gx, gy = pr["grid"]
+    out = []
+    for k in range(len(idx)):
+        if bool(pr["visible"][k]) and int(pr["ntiles"][k]) > 24:
+            tx, ty = int(pr["xy"][k, 0] // 16), int(pr["xy"][k, 1] // 16)
+            if 0 <= tx < gx and 0 <= ty < gy:
+                out.append(ty * gx + tx)
+    return out
 
 
 def test_config1_full_size_on_tile_subset():
-    """BASELINE.json configs[1] at FULL size (200k Gaussians, 512x512, SH deg 0), 24 of 1024 tiles."""
+    """BASELINE.json configs[1] at FULL size (200k Gaussians, 512x512, SH deg 0): 40 of 1024 tiles (3.9 %) incl.
+    corners and edges, two views."""
     sc = make_config(1)
-    tiles = [t for t in range(7, 1024, 43)]
-    _tile_subset_parity(sc, 1, 0, tiles)
+    for v, seed in ((1, 3), (2, 4)):
+        compare_fused(f"configs[1] 200k 512x512 view {v}", sc, v, 0, torch.zeros(3),
+                      tiles=stratified_tiles(32, 32, 12, seed))
 
 
-def test_config2_full_size_on_tile_subset():
-    """BASELINE.json configs[2] at FULL size (1M Gaussians, 1920x1080, SH deg 3), 12 of 8160 tiles."""
+def test_config2_full_size_on_tile_subsets_three_views():
+    """BASELINE.json configs[2] at FULL size (1M Gaussians, 1920x1080, SH deg 3): >= 1 % of the 8160 tiles,
+    stratified over three views, incl. image corners / edges and tiles under Gaussians whose rect spans more than
+    24 tiles (the warp-cooperative counting / emission path)."""
     sc = make_config(2)
-    tiles = [t for t in range(345, 8160, 701)]
-    _tile_subset_parity(sc, 7, 3, tiles)
+    big = enlarge_some(sc, 96, 6.0, seed=5)
+    total = 0
+    for v, seed in ((0, 21), (5, 22), (11, 23)):
+        extra = tiles_under(sc, v, 3, big)[:6]
+        assert len(extra) >= 2, "expected some > 24-tile Gaussians in view"
+        tiles = stratified_tiles(120, 68, 16, seed, extra)
+        total += len(tiles)
+        compare_fused(f"configs[2] 1M 1920x1080 view {v}", sc, v, 3, torch.zeros(3), tiles=tiles)
+    assert total >= 82          # 1 % of 8160
+
+
+def test_config4_4k_on_tile_subset():
+    """BASELINE.json configs[4] geometry (4M Gaussians, 3840x2160 = 32 400 tiles, SH deg 3, R ~ 46 M), one view,
+    tile subset incl. corners and edges."""
+    sc = make_config(4)
+    compare_fused("configs[4] 4M 3840x2160 view 13", sc, 13, 3, torch.zeros(3), tiles=stratified_tiles(240, 135, 24, 31))
 
 
 def test_exact_cull_is_lossless():
@@ -272,7 +248,7 @@ def test_generic_boundary_b2_nonidentity_view_packed_sh():
     m2o = torch.zeros(sc.P, 3, requires_grad=True)
     img_o, radii_o, aux = O.rasterize(po["means"], po["scales"], po["rots"], po["opac"], po["shs"], cam,
                                       means2D=m2o, return_aux=True)
-    w = torch.rand(3, sc.height, sc.width, generator=torch.Generator().manual_seed(1))
+    w = masked_weights((3, sc.height, sc.width), aux["ambiguous"], 1)
     (img_o * w).sum().backward()
     pc = {k: v.to(DEV).clone().requires_grad_(True) for k, v in base.items()}
     m2c = torch.zeros(sc.P, 3, device=DEV, requires_grad=True)
@@ -282,11 +258,13 @@ def test_generic_boundary_b2_nonidentity_view_packed_sh():
     img_c, radii_c = rast(means3D=pc["means"], means2D=m2c, opacities=pc["opac"], shs=pc["shs"],
                           scales=pc["scales"], rotations=pc["rots"])
     (img_c * w.to(DEV)).sum().backward()
-    n_flip = check_image(img_c.detach(), img_o.detach(), aux["ambiguous"])
-    tol = 1e-3 if n_flip == 0 else 1e-2
-    for k in base:
-        assert rel_err(pc[k].grad, po[k].grad) < tol, k
-    assert rel_err(m2c.grad, m2o.grad) < tol
+    st = image_stats(img_c, img_o, aux["ambiguous"])
+    assert_image(st, "B2 non-identity view")
+    ge = {k: rel_err(pc[k].grad, po[k].grad) for k in base}
+    ge["means2D"] = rel_err(m2c.grad, m2o.grad)
+    REPORT.append(dict(case="B2 GaussianRasterizer, non-identity view, packed SH deg 2, scale_modifier 1.3", P=sc.P,
+                       width=sc.width, height=sc.height, **st, grad_rel_err=ge, grad_rel_err_max=max(ge.values())))
+    assert max(ge.values()) < GRAD_TOL, ge
     vis = rast.markVisible(pc["means"].detach())
     assert vis.dtype == torch.bool and vis.shape == (sc.P,)
     # error behaviour of the reference wrapper
@@ -314,16 +292,19 @@ def test_precomputed_colors_and_cov3d():
     leaves_o = [t.clone().requires_grad_(True) for t in (means, cov6, colors, opac)]
     img_o, _, aux = O.rasterize(leaves_o[0], None, None, leaves_o[3], None, cam, colors_precomp=leaves_o[2],
                                 cov3D_precomp=leaves_o[1], return_aux=True)
-    w = torch.rand(3, sc.height, sc.width, generator=torch.Generator().manual_seed(3))
+    w = masked_weights((3, sc.height, sc.width), aux["ambiguous"], 3)
     (img_o * w).sum().backward()
     leaves_c = [t.to(DEV).clone().requires_grad_(True) for t in (means, cov6, colors, opac)]
     rs = settings_for(sc, 0, torch.zeros(3))
     img_c, _ = I.GaussianRasterizer(rs)(means3D=leaves_c[0], means2D=torch.zeros(sc.P, 3, device=DEV),
                                         opacities=leaves_c[3], colors_precomp=leaves_c[2], cov3D_precomp=leaves_c[1])
     (img_c * w.to(DEV)).sum().backward()
-    n_flip = check_image(img_c.detach(), img_o.detach(), aux["ambiguous"])
-    for a, b, name in zip(leaves_c, leaves_o, ("means", "cov3D", "colors", "opac")):
-        assert rel_err(a.grad, b.grad) < (1e-3 if n_flip == 0 else 1e-2), name
+    st = image_stats(img_c, img_o, aux["ambiguous"])
+    assert_image(st, "precomputed colours / cov3D")
+    ge = {name: rel_err(a.grad, b.grad) for a, b, name in zip(leaves_c, leaves_o, ("means", "cov3D", "colors", "opac"))}
+    REPORT.append(dict(case="B2 colors_precomp + cov3D_precomp", P=sc.P, width=sc.width, height=sc.height, **st,
+                       grad_rel_err=ge, grad_rel_err_max=max(ge.values())))
+    assert max(ge.values()) < GRAD_TOL, ge
 
 
 def test_edge_cases_empty_and_culled():
@@ -484,15 +465,25 @@ def test_render_dropin_matches_oracle_and_populates_grads():
     pkg = I.render(cam, pc, _Pipe(), bg, camera_pose=pc.get_RT(0))
     assert set(pkg) == {"render", "viewspace_points", "visibility_filter", "radii"}
     img = pkg["render"]
-    loss = 0.8 * (img - gt.to(DEV)).abs().mean() + 0.2 * (1.0 - I.fused_ssim(img[None], gt.to(DEV)[None]))
-    loss.backward()
-    img_o, radii_o, aux, loss_o, g_o = oracle_run(sc, 3, torch.zeros(3), gt)
-    n_flip = check_image(img.detach(), img_o, aux["ambiguous"])
-    tol = 1e-3 if n_flip == 0 else 1e-2
-    assert rel_err(pc.P.grad[0], g_o["pose"]) < tol
-    assert rel_err(pc._xyz.grad, g_o["xyz"]) < tol
-    assert rel_err(pc._features_rest.grad, g_o["f_rest"]) < tol
-    assert rel_err(pkg["viewspace_points"].grad, g_o["means2D"]) < tol
+    # oracle arm first: its ambiguity mask zeroes the loss weights in both arms
+    co = O.Camera.instantsplat(sc.width, sc.height, sc.fovx, sc.fovy, sh_degree=3)
+    po = {k: v.clone().requires_grad_(True) for k, v in sc.params.items()}
+    pose_o = sc.poses[0].clone().requires_grad_(True)
+    m2o = torch.zeros(sc.P, 3, requires_grad=True)
+    img_o, _, aux = O.render_instantsplat(po["xyz"], po["rotation"], po["scaling"], po["opacity"], po["f_dc"], po["f_rest"],
+                                          pose_o, co, means2D=m2o, return_aux=True)
+    assert_image(image_stats(img, img_o, aux["ambiguous"]), "render() drop-in")
+    # the reference's loss expression (train.py:171-176) supplies dL/dimage; flagged pixels get zero weight
+    im = img.detach().clone().requires_grad_(True)
+    (0.8 * (im - gt.to(DEV)).abs().mean() + 0.2 * (1.0 - I.fused_ssim(im[None], gt.to(DEV)[None]))).backward()
+    w = im.grad * (~aux["ambiguous"]).to(DEV)[None]
+    w = w / w.abs().max()
+    (img * w).sum().backward()
+    (img_o * w.cpu()).sum().backward()
+    ge = dict(pose=rel_err(pc.P.grad[0], pose_o.grad), xyz=rel_err(pc._xyz.grad, po["xyz"].grad),
+              f_rest=rel_err(pc._features_rest.grad, po["f_rest"].grad),
+              viewspace_points=rel_err(pkg["viewspace_points"].grad, m2o.grad))
+    assert max(ge.values()) < GRAD_TOL, ge
     assert pkg["visibility_filter"].dtype == torch.bool
 
 

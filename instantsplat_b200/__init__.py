@@ -15,4 +15,5 @@ from .renderer import render  # noqa: F401
 from .ssim import fused_ssim, fused_training_loss  # noqa: F401
 from .per_point_adam import PerPointAdam  # noqa: F401
 from .trainer import JointTrainer, OptimConfig  # noqa: F401
-from .model import PipelineDefaults, SimpleGaussianModel  # noqa: F401
+from .model import GaussianModel, PipelineDefaults, SimpleGaussianModel, optimization_defaults  # noqa: F401
+from .knn import distCUDA2  # noqa: F401

@@ -12,6 +12,15 @@ import torch
 
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_fused
 
+# FUSED = True : the whole body (pose pre-transform, activations, feature cat, rasterizer) is ONE call into the library.
+# FUSED = False: the reference's own body is restated op for op (PyTorch pose pre-transform -> GaussianRasterizer), i.e.
+#                what an UNCHANGED /root/reference/gaussian_renderer/__init__.py does on top of the rasterizer shim;
+#                bench.py times it as `dropin_unchanged`.  Env GSB_FUSED_RENDER=0 selects it process-wide.
+import os as _os
+
+FUSED = _os.environ.get("GSB_FUSED_RENDER", "1") != "0"
+_RASTERIZER = (GaussianRasterizationSettings, GaussianRasterizer)    # replaceable by the CPU tests
+
 _const_cache = {}
 
 
@@ -54,13 +63,14 @@ def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_
     tanfovx = math.tan(viewpoint_camera.FoVx * 0.5)
     tanfovy = math.tan(viewpoint_camera.FoVy * 0.5)
     w2c, campos = _identity_consts(xyz.device)
+    Settings, Rasterizer = _RASTERIZER
     # identity view: projmatrix = I @ P^T (reference :55-59)
-    raster_settings = GaussianRasterizationSettings(
+    raster_settings = Settings(
         image_height=int(viewpoint_camera.image_height), image_width=int(viewpoint_camera.image_width),
         tanfovx=tanfovx, tanfovy=tanfovy, bg=bg_color, scale_modifier=scaling_modifier, viewmatrix=w2c,
         projmatrix=viewpoint_camera.projection_matrix, sh_degree=pc.active_sh_degree, campos=campos,
         prefiltered=False, debug=bool(getattr(pipe, "debug", False)))
-    fused = (override_color is None and not getattr(pipe, "compute_cov3D_python", False)
+    fused = (FUSED and override_color is None and not getattr(pipe, "compute_cov3D_python", False)
              and not getattr(pipe, "convert_SHs_python", False))
     if fused:
         rendered_image, radii = rasterize_fused(pc._xyz, pc._rotation, pc._scaling, pc._opacity,
@@ -68,9 +78,10 @@ def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_
                                                 screenspace_points, raster_settings)
     else:
         rel_w2c = get_camera_from_tensor(camera_pose)
-        homo = torch.cat((pc._xyz, torch.ones(xyz.shape[0], 1, device=xyz.device)), dim=1)
+        gaussians_xyz, gaussians_rot = pc._xyz.clone(), pc._rotation.clone()            # reference :83-84
+        homo = torch.cat((gaussians_xyz, torch.ones(xyz.shape[0], 1, device=xyz.device)), dim=1)
         means3D = (rel_w2c @ homo.T).T[:, :3]
-        rots = quadmultiply(camera_pose[:4], pc._rotation)
+        rots = quadmultiply(camera_pose[:4], gaussians_rot)
         scales = rotations = cov3D_precomp = shs = colors_precomp = None
         if getattr(pipe, "compute_cov3D_python", False):
             cov3D_precomp = pc.get_covariance(scaling_modifier)
@@ -84,7 +95,7 @@ def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_
                 shs = pc.get_features
         else:
             colors_precomp = override_color
-        rasterizer = GaussianRasterizer(raster_settings=raster_settings)
+        rasterizer = Rasterizer(raster_settings=raster_settings)
         rendered_image, radii = rasterizer(means3D=means3D, means2D=screenspace_points, shs=shs,
                                            colors_precomp=colors_precomp, opacities=pc.get_opacity,
                                            scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp)

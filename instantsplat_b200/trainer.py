@@ -419,6 +419,86 @@ class JointTrainer:
             self._run_iteration(view, gt, do_opt)
             assert self._settle()
 
+    # ---- densify / prune / opacity reset on the flat buffers -----------------------
+    # Semantics of /root/reference/scene/gaussian_model.py: prune_points (:359-374) keeps the surviving rows of every
+    # parameter AND of both Adam moments; densification_postfix (:399-418) appends rows with zero moments;
+    # reset_opacity (:280-283) clamps the opacity to 0.01 (in logit space) and zeroes that tensor's moments.  The
+    # optimizer's step counter is untouched by all three, as in the reference (state["step"] survives the surgery).
+    def _resize(self, new_P: int, rows) -> None:
+        """rows(name, old_param_view, old_m_view, old_v_view) -> (param, m, v) tensors of shape [new_P, k]."""
+        if self.exchange == "fused_p2p":
+            raise _lib.GsbError("changing the number of Gaussians is not supported with peer-memory buffers "
+                                "(exchange='fused_p2p'); use exchange='allreduce'")
+        L = _lib.lib()
+        new = {name: rows(name, self.view(self.params, name), self.view(self.exp_avg, name),
+                          self.view(self.exp_avg_sq, name)) for name, _ in SEGMENTS}
+        offs, total = {}, 0
+        for name, k in SEGMENTS:
+            offs[name] = total
+            total += _align(new_P * k)
+        self.P, self.offs, self.total = new_P, offs, total
+        self.params = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.grads = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        for name, k in SEGMENTS:
+            p_, m_, v_ = new[name]
+            self.view(self.params, name).copy_(p_.reshape(new_P, k))
+            self.view(self.exp_avg, name).copy_(m_.reshape(new_P, k))
+            self.view(self.exp_avg_sq, name).copy_(v_.reshape(new_P, k))
+        self.geom_bytes = L.gsb_geom_bytes(new_P)
+        self.geom = torch.empty(self.geom_bytes, dtype=torch.uint8, device=self.dev)
+        self.radii = torch.empty(new_P, dtype=torch.int32, device=self.dev)
+        self._status_dev = L.gsb_status_device(self.geom.data_ptr(), new_P)
+        so = self._status_dev - self.geom.data_ptr()
+        self._status_t = self.geom[so:so + 32].view(torch.int32)
+        self.cap = 0                                  # the next forward sizes the binning buffer from the new count
+        self._keep = None
+
+    def _set_per_point_lr(self, values: Optional[torch.Tensor]) -> None:
+        if values is None:
+            self.per_point_lr = None
+            return
+        ppl = torch.ones(_align(self.P * 3) // 3 + 1, dtype=torch.float32, device=self.dev)
+        ppl[:self.P] = values.to(self.dev).float().reshape(self.P)
+        self.per_point_lr = ppl
+
+    def prune_points(self, mask: torch.Tensor) -> None:
+        """Remove the Gaussians where `mask` [P] is True."""
+        keep = ~mask.to(self.dev).bool()
+        ppl = None if self.per_point_lr is None else self.per_point_lr[:self.P][keep]
+        self._resize(int(keep.sum()), lambda name, p, m, v: (p[keep], m[keep], v[keep]))
+        self._set_per_point_lr(ppl)
+
+    def densification_postfix(self, new_xyz, new_features_dc, new_features_rest, new_opacities, new_scaling,
+                              new_rotation, new_per_point_lr=None) -> None:
+        """Append Gaussians; their Adam moments start at zero."""
+        ext = dict(xyz=new_xyz, f_dc=new_features_dc, f_rest=new_features_rest, opacity=new_opacities,
+                   scaling=new_scaling, rotation=new_rotation)
+        n_new = int(new_xyz.shape[0])
+        k_of = dict(SEGMENTS)
+        ppl = None
+        if self.per_point_lr is not None:
+            add = torch.ones(n_new, device=self.dev) if new_per_point_lr is None else \
+                new_per_point_lr.to(self.dev).float().reshape(n_new)
+            ppl = torch.cat((self.per_point_lr[:self.P], add))
+
+        def rows(name, p, m, v):
+            e = ext[name].to(self.dev).float().reshape(n_new, k_of[name])
+            z = torch.zeros_like(e)
+            return torch.cat((p, e)), torch.cat((m, z)), torch.cat((v, z))
+
+        self._resize(self.P + n_new, rows)
+        self._set_per_point_lr(ppl)
+
+    def reset_opacity(self) -> None:
+        op = self.view(self.params, "opacity")
+        cur = torch.sigmoid(op)
+        new = torch.min(cur, torch.full_like(cur, 0.01))
+        op.copy_(torch.log(new / (1 - new)))
+        self.view(self.exp_avg, "opacity").zero_()
+        self.view(self.exp_avg_sq, "opacity").zero_()
+
     def blend_stats(self, view: int, gt: Optional[torch.Tensor] = None) -> Dict[str, int]:
         """Pair statistics of the blend kernels for one forward+backward of `view` (instrumented re-run of the same
         kernels, outside any timed region): evaluated / contributing (pixel, Gaussian) pairs."""

@@ -150,6 +150,22 @@ GSB_API int gsb_loss_forward(int32_t C, int32_t H, int32_t W, const float* img, 
 GSB_API int gsb_loss_backward(int32_t C, int32_t H, int32_t W, const float* img, const float* gt,
                       const float* maps, float lambda_dssim, float* dL_dimg, gsb_stream_t stream);
 
+/* ---- pose-only tracking mode (render.py:99-170: Gaussians frozen, Adam on the 7 pose parameters of one view) ----
+ * Masked L1 (utils/loss_utils.py:17-23 with the mask of render.py:137-138), forward and backward in one pass:
+ * mask = (img > threshold) per element; sums[0] += sum |img-gt|*mask, sums[1] += sum mask (double[2], caller zeroes);
+ * dL_dimg = sign(img-gt)*mask -- NOT yet divided by sum(mask): gsb_track_step applies that factor to dL/dpose. */
+GSB_API int gsb_l1_mask_fwd_bwd(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, float threshold,
+                                double* sums, float* dL_dimg, gsb_stream_t stream);
+/* One optimiser step of render.py:118-151 entirely on the device (all pointers are device pointers):
+ * loss = sums2[0]/sums2[1]; g = dpose7_raw/sums2[1] + weight_decay*pose; torch.optim.Adam update with step count
+ * `step` (1-based) and learning rates lr_q (pose[0..3]) / lr_T (pose[4..6]) -- the caller evaluates the cosine
+ * schedule on the host; then, if loss < best8[0]: best8 = {loss, pose AFTER the step} (render.py:146-151).
+ * loss_out (optional) receives the loss.  gsb_backward with only GsbGrads.dL_dpose set produces dpose7_raw through a
+ * blend backward specialised for this mode (8 accumulated values per Gaussian instead of 9). */
+GSB_API int gsb_track_step(float* pose7, const float* dpose7_raw, const double* sums2, float* exp_avg7,
+                           float* exp_avg_sq7, float* best8, float* loss_out, int32_t step, float lr_q, float lr_T,
+                           float beta1, float beta2, float eps, float weight_decay, gsb_stream_t stream);
+
 /* Per-point Adam (scene/per_point_adam.py:34-98), n tensors in one launch. */
 typedef struct GsbAdamTensor {
   float* param;

@@ -173,6 +173,39 @@ __device__ __forceinline__ void warp_reduce9(float* v, int lane) {
   v[8] = e;
 }
 
+// Same butterfly without the ninth value.
+__device__ __forceinline__ void warp_reduce8(float* v, int lane) {
+  const unsigned full = 0xffffffffu;
+  float b[4], c[2], d;
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float send = hi ? v[k] : v[k + 4];
+      float keep = hi ? v[k + 4] : v[k];
+      b[k] = keep + __shfl_xor_sync(full, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float send = hi ? b[k] : b[k + 2];
+      float keep = hi ? b[k + 2] : b[k];
+      c[k] = keep + __shfl_xor_sync(full, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+    float send = hi ? c[0] : c[1];
+    float keep = hi ? c[1] : c[0];
+    d = keep + __shfl_xor_sync(full, send, 4);
+  }
+  d += __shfl_xor_sync(full, d, 2);
+  d += __shfl_xor_sync(full, d, 1);
+  v[0] = d;
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_blend_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
             const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
@@ -250,15 +283,14 @@ k_blend_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, con
             dL_dalpha *= T;
             last_alpha = pe.alpha;
             dL_dalpha -= T_final * inv1ma * bg_dot;
-            const float dL_dG = e1.y * dL_dalpha;
-            const float gdx = pe.G * pe.dx, gdy = pe.G * pe.dy;
-            // -A = 2 ln2 A', -B = ln2 B', -C = 2 ln2 C'
-            v[0] = dL_dG * kLn2 * (2.f * gdx * e0.z + gdy * e0.w);
-            v[1] = dL_dG * kLn2 * (2.f * gdy * e1.x + gdx * e0.w);
-            v[2] = -0.5f * gdx * pe.dx * dL_dG;
-            v[3] = -gdx * pe.dy * dL_dG;
-            v[4] = -0.5f * gdy * pe.dy * dL_dG;
-            v[5] = pe.G * dL_dalpha;
+            // raw moments of w = dL/dalpha * opacity * G (constants applied in k_preprocess_bwd, see k_blend_bwd2)
+            const float w = e1.y * pe.G * dL_dalpha;
+            v[0] = w * pe.dx;
+            v[1] = w * pe.dy;
+            v[2] = v[0] * pe.dx;
+            v[3] = v[0] * pe.dy;
+            v[4] = v[1] * pe.dy;
+            v[5] = w;
             v[6] = dchannel_dcolor * dLr;
             v[7] = dchannel_dcolor * dLg;
             v[8] = dchannel_dcolor * dLb;
@@ -471,7 +503,10 @@ k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
   }
 }
 
-template <bool BULK, bool STATS = false>
+// POSE_ONLY (tracking mode, render.py:99-170: Gaussians frozen): dL/dopacity is not needed, so the moment S w is
+// dropped and dL/db takes its slot -- eight values, no ninth reduction chain, no scalar RED; k_preprocess_bwd is
+// told about the layout (dacc[5] = dL/db, dacc[8] unused).
+template <bool BULK, bool STATS = false, bool POSE_ONLY = false>
 __global__ void __launch_bounds__(kThreads2, GSB_BWD_MINB)
 k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
              const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
@@ -561,16 +596,16 @@ k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
           const float c1 = e0.w * dx, c0 = e0.z * dx * dx;
           const float2 pw = __ffma2_rn(dy, __ffma2_rn(f2s(e1.x), dy, f2s(c1)), f2s(c0));
           const float2 G = f2(ex2_approx(pw.x), ex2_approx(pw.y));
-          float2 al = __fmul2_rn(f2s(e1.y), G);
-          al.x = fminf(0.99f, al.x); al.y = fminf(0.99f, al.y);
-          const bool vA = inA && pos < lcA && pw.x <= 0.f && al.x >= kAlphaMin;
-          const bool vB = inB && pos < lcB && pw.y <= 0.f && al.y >= kAlphaMin;
+          const float2 alu = __fmul2_rn(f2s(e1.y), G);           // opacity * G (unclamped: the straight-through alpha)
+          const bool vA = inA && pos < lcA && pw.x <= 0.f && alu.x >= kAlphaMin;      // min(0.99, a) >= 1/255 <=> a >= 1/255
+          const bool vB = inB && pos < lcB && pw.y <= 0.f && alu.y >= kAlphaMin;
           if (STATS) { ++st_iter; st_valid += (vA ? 1u : 0u) + (vB ? 1u : 0u); }
           if (!__any_sync(0xffffffffu, vA || vB)) continue;
           if (STATS) ++st_red;
           const float4 c = sm2[b + k];
-          // masked alpha: an invalid pixel behaves as alpha = 0 (T, accumulator and gradients unchanged)
-          const float2 am = f2(vA ? al.x : 0.f, vB ? al.y : 0.f);
+          // masked alphas: an invalid pixel behaves as alpha = 0 (T, accumulator and every moment unchanged)
+          const float2 aw = f2(vA ? alu.x : 0.f, vB ? alu.y : 0.f);              // weight of the moments (unclamped)
+          const float2 am = f2(fminf(0.99f, aw.x), fminf(0.99f, aw.y));          // blending alpha (clamped)
           const float2 one_m = __ffma2_rn(am, f2s(-1.f), f2s(1.f));
           const float2 inv = f2(rcp_approx(one_m.x), rcp_approx(one_m.y));
           T = __fmul2_rn(T, inv);
@@ -583,34 +618,32 @@ k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
           float2 da = __ffma2_rn(d_b, dLb, __ffma2_rn(d_g, dLg, __fmul2_rn(d_r, dLr)));
           da = __fmul2_rn(da, T);
           da = __ffma2_rn(f2(-tf_bg.x, -tf_bg.y), inv, da);
-          da.x = vA ? da.x : 0.f; da.y = vB ? da.y : 0.f;
           acc_r = __ffma2_rn(am, d_r, acc_r);
           acc_g = __ffma2_rn(am, d_g, acc_g);
           acc_b = __ffma2_rn(am, d_b, acc_b);
-          const float2 dG = __fmul2_rn(f2s(e1.y), da);           // dL/dG = opacity * dL/dalpha
-          const float2 gdG = __fmul2_rn(G, dG);                  // G * dL/dG
-          const float2 gy = __fmul2_rn(gdG, dy);                 // G dL/dG dy
-          const float gxs = (gdG.x + gdG.y) * dx;                // sum over the two pixels of G dL/dG dx
-          const float gys = gy.x + gy.y;
+          // w = dL/dalpha * opacity * G, zero on invalid pixels through aw.  The warp accumulates the raw moments of w;
+          // the per-Gaussian constants (conic, 1/opacity) are applied once in k_preprocess_bwd.
+          const float2 w = __fmul2_rn(aw, da);
+          const float2 wy = __fmul2_rn(w, dy);
+          const float ws = w.x + w.y;
           float v[9];
-          v[0] = kLn2 * (2.f * gxs * e0.z + gys * e0.w);
-          v[1] = kLn2 * (2.f * gys * e1.x + gxs * e0.w);
-          v[2] = -0.5f * gxs * dx;
-          v[3] = -dx * gys;
-          v[4] = -0.5f * (gy.x * dy.x + gy.y * dy.y);
-          v[5] = G.x * da.x + G.y * da.y;
-          const float dcs_r = dcol.x * dLr.x + dcol.y * dLr.y;
-          v[6] = dcs_r;
+          v[0] = ws * dx;                                        // S w dx
+          v[1] = wy.x + wy.y;                                    // S w dy
+          v[2] = v[0] * dx;                                      // S w dx^2
+          v[3] = v[1] * dx;                                      // S w dx dy
+          v[4] = wy.x * dy.x + wy.y * dy.y;                      // S w dy^2
+          v[6] = dcol.x * dLr.x + dcol.y * dLr.y;
           v[7] = dcol.x * dLg.x + dcol.y * dLg.y;
           v[8] = dcol.x * dLb.x + dcol.y * dLb.y;
-          warp_reduce9(v, lane);
+          v[5] = POSE_ONLY ? v[8] : ws;                          // S w (or dL/db in the 8-value layout)
+          if (POSE_ONLY) warp_reduce8(v, lane); else warp_reduce9(v, lane);
           const float a1 = __shfl_down_sync(0xffffffffu, v[0], 4);
           const float a2 = __shfl_down_sync(0xffffffffu, v[0], 8);
           const float a3 = __shfl_down_sync(0xffffffffu, v[0], 12);
           float* dst = dacc + (size_t)__float_as_uint(e1.w) * 12;
           if (!STATS) {
             if ((lane & 15) == 0) red_add_v4(dst + (lane >> 2), v[0], a1, a2, a3);
-            if (lane == 1) atomicAdd(dst + 8, v[8]);
+            if (!POSE_ONLY && lane == 1) atomicAdd(dst + 8, v[8]);
           }
         }
       }
@@ -650,11 +683,14 @@ int gsb_launch_blend_fwd(const BinView& bv, const ImgView& iv, const float* bg, 
 }
 
 int gsb_launch_blend_bwd(const BinView& bv, const ImgView& iv, const float* bg, int W, int H, const float* dL_dout,
-                         float* dacc, cudaStream_t st) {
+                         float* dacc, bool pose_only, cudaStream_t st) {
   const int gx = (W + kBlock - 1) / kBlock, gy = (H + kBlock - 1) / kBlock;
   ProfScope ps(GSB_K_BLEND_BWD, st);
   const int ver = gsb_option_blend_version(), bulk = gsb_option_stage_bulk();
-  if (ver == 2 && bulk)
+  if (pose_only)
+    k_blend_bwd2<true, false, true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, iv.final_T,
+                                                                   iv.n_contrib, dL_dout, dacc);
+  else if (ver == 2 && bulk)
     k_blend_bwd2<true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, iv.final_T,
                                                       iv.n_contrib, dL_dout, dacc);
   else if (ver == 2)

@@ -158,5 +158,6 @@ int gsb_launch_binning(int P, const gsb::GeomView& gv, const gsb::BinView& bv, i
                        uint32_t cap, cudaStream_t st);
 int gsb_launch_blend_fwd(const gsb::BinView& bv, const gsb::ImgView& iv, const float* bg, int W, int H,
                          float* out_color, cudaStream_t st);
+// pose_only: 8-value accumulator layout (dacc[5] = dL/db, no dL/dopacity), see k_blend_bwd2
 int gsb_launch_blend_bwd(const gsb::BinView& bv, const gsb::ImgView& iv, const float* bg, int W, int H,
-                         const float* dL_dout, float* dacc, cudaStream_t st);
+                         const float* dL_dout, float* dacc, bool pose_only, cudaStream_t st);

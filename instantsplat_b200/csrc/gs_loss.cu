@@ -33,15 +33,17 @@ constexpr float C2 = 0.03f * 0.03f;
 
 // normalised 1-D window exp(-(x-5)^2 / 4.5), built like loss_utils.gaussian() (fp32 sum)
 __constant__ float c_win[11];
-bool g_win_ready = false;
+bool g_win_ready[64] = {};     // __constant__ memory is per device
 
 int ensure_window() {
-  if (g_win_ready) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (dev >= 0 && dev < 64 && g_win_ready[dev]) return 0;
   float w[11], s = 0.f;
   for (int i = 0; i < 11; ++i) { w[i] = (float)exp(-(double)((i - 5) * (i - 5)) / 4.5); s += w[i]; }
   for (int i = 0; i < 11; ++i) w[i] /= s;
   if (cudaMemcpyToSymbol(c_win, w, sizeof(w)) != cudaSuccess) return -1;
-  g_win_ready = true;
+  if (dev >= 0 && dev < 64) g_win_ready[dev] = true;
   return 0;
 }
 
@@ -60,9 +62,9 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return r;   // valid in thread 0
 }
 
-// Stage a (TH+10) x (TW+10) halo of one plane into shared memory (zero 'same' padding): one warp per
-// row, lanes along x (two coalesced accesses per row).  Fully unrolled with all global loads issued
-// before the first shared store, so a lane has 8 loads in flight per plane.
+// Stage the (TH+10) x (TW+10) halo of TWO planes into shared memory as interleaved float2 {a, b} (zero 'same'
+// padding): one warp per row, lanes along x (two coalesced accesses per row and plane).  Fully unrolled with all
+// global loads issued before the first shared store, so a lane has 16 loads in flight.
 constexpr int kRowsPerWarp = (EH + 7) / 8;   // 4
 struct HaloRegs { float a[kRowsPerWarp], b[kRowsPerWarp]; };
 
@@ -81,26 +83,43 @@ __device__ __forceinline__ void halo_load(HaloRegs& h, const float* __restrict__
     h.b[i] = (yin && xb_in) ? __ldg(row + xb) : 0.f;
   }
 }
-__device__ __forceinline__ void halo_store(const HaloRegs& h, float (*dst)[EWP]) {
+// dst[r][x] = {p.(x), q.(x)}
+__device__ __forceinline__ void halo_store2(const HaloRegs& p, const HaloRegs& q, float2 (*dst)[EWP]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i < kRowsPerWarp; ++i) {
     const int r = warp + 8 * i;
     if (r < EH) {
-      dst[r][lane] = h.a[i];
-      if (lane < EWP - 32) dst[r][32 + lane] = h.b[i];
+      dst[r][lane] = make_float2(p.a[i], q.a[i]);
+      if (lane < EWP - 32) dst[r][32 + lane] = make_float2(p.b[i], q.b[i]);
     }
   }
 }
-// Register-tiled separable 11-tap filter.  Horizontal: thread -> (row, 4 adjacent columns), inputs
-// fetched with four 128-bit shared loads.  Vertical: thread -> (column, 2 adjacent rows).
+__device__ __forceinline__ void halo_store1(const HaloRegs& p, float (*dst)[EWP]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) {
+    const int r = warp + 8 * i;
+    if (r < EH) {
+      dst[r][lane] = p.a[i];
+      if (lane < EWP - 32) dst[r][32 + lane] = p.b[i];
+    }
+  }
+}
+__device__ __forceinline__ float2 bcast(float w) { return make_float2(w, w); }
+
+// Register-tiled separable 11-tap filter, packed f32x2 arithmetic (Blackwell FFMA2): the five windowed statistics
+// are carried as {E[a], E[b]}, {E[a^2], E[b^2]} (two packed accumulators) and E[ab] (scalar), i.e. 3 FMA-class
+// instructions per tap and output instead of 5.  Horizontal: thread -> (row, 4 adjacent columns), inputs fetched
+// with seven 128-bit shared loads.  Vertical: thread -> (column, 2 adjacent rows).
 // img planes [BC][H][W].  maps (optional) [3][BC][H][W].  sums[0] += sum|a-b| (if do_l1), sums[1] += sum ssim.
 __global__ void __launch_bounds__(256, 4)
 k_ssim_fwd(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
            double* __restrict__ sums, float* __restrict__ maps, size_t plane_total, int do_l1) {
-  __shared__ __align__(16) float sA[EH][EWP];
-  __shared__ __align__(16) float sB[EH][EWP];
-  __shared__ float sH[5][EH][HS];
+  __shared__ __align__(16) float2 sAB[EH][EWP];
+  __shared__ __align__(16) float2 sH1[EH][HS];     // {E_h[a], E_h[b]}
+  __shared__ __align__(16) float2 sH2[EH][HS];     // {E_h[a^2], E_h[b^2]}
+  __shared__ float sH3[EH][HS];                    // E_h[ab]
   __shared__ float red[8];
   const int bc = blockIdx.z;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -108,63 +127,68 @@ k_ssim_fwd(int H, int W, const float* __restrict__ img1, const float* __restrict
     HaloRegs ha, hb;
     halo_load(ha, img1 + (size_t)bc * H * W, H, W, x0, y0);
     halo_load(hb, img2 + (size_t)bc * H * W, H, W, x0, y0);
-    halo_store(ha, sA);
-    halo_store(hb, sB);
+    halo_store2(ha, hb, sAB);
   }
   __syncthreads();
   if (threadIdx.x < EH * (TW / 4)) {
     const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
-    float a[16], b[16];
+    float2 a1[4], a2[4];
+    float a3[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 va = *reinterpret_cast<const float4*>(&sA[r][c0 + 4 * q]);
-      float4 vb = *reinterpret_cast<const float4*>(&sB[r][c0 + 4 * q]);
-      a[4 * q] = va.x; a[4 * q + 1] = va.y; a[4 * q + 2] = va.z; a[4 * q + 3] = va.w;
-      b[4 * q] = vb.x; b[4 * q + 1] = vb.y; b[4 * q + 2] = vb.z; b[4 * q + 3] = vb.w;
-    }
-    float acc[5][4];
+    for (int o = 0; o < 4; ++o) { a1[o] = make_float2(0.f, 0.f); a2[o] = make_float2(0.f, 0.f); a3[o] = 0.f; }
 #pragma unroll
-    for (int q = 0; q < 5; ++q)
+    for (int q = 0; q < 7; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(&sAB[r][c0 + 2 * q]);
 #pragma unroll
-      for (int o = 0; o < 4; ++o) acc[q][o] = 0.f;
+      for (int h = 0; h < 2; ++h) {
+        const int i = 2 * q + h;
+        const float2 ab = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+        const float2 sq = __fmul2_rn(ab, ab);
+        const float x = ab.x * ab.y;
 #pragma unroll
-    for (int i = 0; i < 14; ++i) {
-      const float av = a[i], bv = b[i], aa = av * av, bb = bv * bv, ab = av * bv;
-#pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        const int t = i - o;
-        if (t >= 0 && t < 11) {
-          const float w = c_win[t];
-          acc[0][o] += w * av; acc[1][o] += w * bv; acc[2][o] += w * aa; acc[3][o] += w * bb; acc[4][o] += w * ab;
+        for (int o = 0; o < 4; ++o) {
+          const int t = i - o;
+          if (t >= 0 && t < 11) {
+            const float w = c_win[t];
+            a1[o] = __ffma2_rn(bcast(w), ab, a1[o]);
+            a2[o] = __ffma2_rn(bcast(w), sq, a2[o]);
+            a3[o] = fmaf(w, x, a3[o]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int q = 0; q < 5; ++q)
-#pragma unroll
-      for (int o = 0; o < 4; ++o) sH[q][r][c0 + o] = acc[q][o];
+    for (int o = 0; o < 4; ++o) { sH1[r][c0 + o] = a1[o]; sH2[r][c0 + o] = a2[o]; sH3[r][c0 + o] = a3[o]; }
   }
   __syncthreads();
   const int tx = threadIdx.x & 31, ty = (threadIdx.x >> 5) * 2;
-  float v[5][12];
+  float2 m[2], e[2];
+  float e12[2];
 #pragma unroll
-  for (int q = 0; q < 5; ++q)
+  for (int o = 0; o < 2; ++o) { m[o] = make_float2(0.f, 0.f); e[o] = make_float2(0.f, 0.f); e12[o] = 0.f; }
 #pragma unroll
-    for (int i = 0; i < 12; ++i) v[q][i] = sH[q][ty + i][tx];
+  for (int i = 0; i < 12; ++i) {
+    const float2 v1 = sH1[ty + i][tx], v2 = sH2[ty + i][tx];
+    const float v3 = sH3[ty + i][tx];
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      const int t = i - o;
+      if (t >= 0 && t < 11) {
+        const float w = c_win[t];
+        m[o] = __ffma2_rn(bcast(w), v1, m[o]);
+        e[o] = __ffma2_rn(bcast(w), v2, e[o]);
+        e12[o] = fmaf(w, v3, e12[o]);
+      }
+    }
+  }
   float ssim_v = 0.f, l1_v = 0.f;
 #pragma unroll
   for (int o = 0; o < 2; ++o) {
     const int x = x0 + tx, y = y0 + ty + o;
-    float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
-#pragma unroll
-    for (int t = 0; t < 11; ++t) {
-      const float w = c_win[t];
-      mu1 += w * v[0][o + t]; mu2 += w * v[1][o + t]; e11 += w * v[2][o + t]; e22 += w * v[3][o + t];
-      e12 += w * v[4][o + t];
-    }
     if (x < W && y < H) {
+      const float mu1 = m[o].x, mu2 = m[o].y;
       float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
-      float s1 = e11 - mu1_sq, s2 = e22 - mu2_sq, s12 = e12 - mu12;
+      float s1 = e[o].x - mu1_sq, s2 = e[o].y - mu2_sq, s12 = e12[o] - mu12;
       float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2, B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
       float inv = 1.f / (B1 * B2);
       float sv = A1 * A2 * inv;
@@ -175,7 +199,7 @@ k_ssim_fwd(int H, int W, const float* __restrict__ img1, const float* __restrict
         maps[plane_total + off] = -sv / B2;                                       // d/dE[x^2]
         maps[2 * plane_total + off] = 2.f * A1 * inv;                             // d/dE[xy]
       }
-      if (do_l1) l1_v += fabsf(sA[ty + o + HALO][tx + HALO] - sB[ty + o + HALO][tx + HALO]);
+      if (do_l1) { const float2 c = sAB[ty + o + HALO][tx + HALO]; l1_v += fabsf(c.x - c.y); }
     }
   }
   float s = block_sum(ssim_v, red);
@@ -188,12 +212,15 @@ k_ssim_fwd(int H, int W, const float* __restrict__ img1, const float* __restrict
 }
 
 // out = ssim_scale * (conv(m_mu) + 2 x conv(m_s1) + y conv(m_s12)) [* *dyn_scale] + l1_scale * sign(x-y)
+// The first two maps travel as one packed float2 through both filter passes (2 FMA-class instructions per tap).
 __global__ void __launch_bounds__(256, 5)
 k_ssim_bwd(int H, int W, const float* __restrict__ img1, const float* __restrict__ img2,
            const float* __restrict__ maps, size_t plane_total, float ssim_scale,
            const float* __restrict__ dyn_scale, float l1_scale, float* __restrict__ out) {
-  __shared__ __align__(16) float sM[3][EH][EWP];
-  __shared__ float sH[3][EH][HS];
+  __shared__ __align__(16) float2 sM12[EH][EWP];
+  __shared__ __align__(16) float sM3[EH][EWP];
+  __shared__ __align__(16) float2 sH12[EH][HS];
+  __shared__ float sH3[EH][HS];
   const int bc = blockIdx.z;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const size_t pbase = (size_t)bc * H * W;
@@ -202,54 +229,71 @@ k_ssim_bwd(int H, int W, const float* __restrict__ img1, const float* __restrict
     halo_load(h0, maps + pbase, H, W, x0, y0);
     halo_load(h1, maps + plane_total + pbase, H, W, x0, y0);
     halo_load(h2, maps + 2 * plane_total + pbase, H, W, x0, y0);
-    halo_store(h0, sM[0]);
-    halo_store(h1, sM[1]);
-    halo_store(h2, sM[2]);
+    halo_store2(h0, h1, sM12);
+    halo_store1(h2, sM3);
   }
   __syncthreads();
   if (threadIdx.x < EH * (TW / 4)) {
     const int r = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 4;
+    float2 a12[4];
+    float a3[4];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      float a[16];
+    for (int o = 0; o < 4; ++o) { a12[o] = make_float2(0.f, 0.f); a3[o] = 0.f; }
+    float m3[16];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float4 va = *reinterpret_cast<const float4*>(&sM[q][r][c0 + 4 * u]);
-        a[4 * u] = va.x; a[4 * u + 1] = va.y; a[4 * u + 2] = va.z; a[4 * u + 3] = va.w;
-      }
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int u = 0; u < 4; ++u) {
+      const float4 v = *reinterpret_cast<const float4*>(&sM3[r][c0 + 4 * u]);
+      m3[4 * u] = v.x; m3[4 * u + 1] = v.y; m3[4 * u + 2] = v.z; m3[4 * u + 3] = v.w;
+    }
 #pragma unroll
-      for (int i = 0; i < 14; ++i)
+    for (int q = 0; q < 7; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(&sM12[r][c0 + 2 * q]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = 2 * q + h;
+        const float2 p = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
           const int t = i - o;
-          if (t >= 0 && t < 11) acc[o] += c_win[t] * a[i];
+          if (t >= 0 && t < 11) {
+            const float w = c_win[t];
+            a12[o] = __ffma2_rn(bcast(w), p, a12[o]);
+            a3[o] = fmaf(w, m3[i], a3[o]);
+          }
         }
-#pragma unroll
-      for (int o = 0; o < 4; ++o) sH[q][r][c0 + o] = acc[o];
+      }
     }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { sH12[r][c0 + o] = a12[o]; sH3[r][c0 + o] = a3[o]; }
   }
   __syncthreads();
   const int tx = threadIdx.x & 31, ty = (threadIdx.x >> 5) * 2;
-  float v[3][12];
+  float2 g12[2];
+  float g3[2];
 #pragma unroll
-  for (int q = 0; q < 3; ++q)
+  for (int o = 0; o < 2; ++o) { g12[o] = make_float2(0.f, 0.f); g3[o] = 0.f; }
 #pragma unroll
-    for (int i = 0; i < 12; ++i) v[q][i] = sH[q][ty + i][tx];
+  for (int i = 0; i < 12; ++i) {
+    const float2 v12 = sH12[ty + i][tx];
+    const float v3 = sH3[ty + i][tx];
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      const int t = i - o;
+      if (t >= 0 && t < 11) {
+        const float w = c_win[t];
+        g12[o] = __ffma2_rn(bcast(w), v12, g12[o]);
+        g3[o] = fmaf(w, v3, g3[o]);
+      }
+    }
+  }
   const float sc = ssim_scale * (dyn_scale ? *dyn_scale : 1.f);
 #pragma unroll
   for (int o = 0; o < 2; ++o) {
     const int x = x0 + tx, y = y0 + ty + o;
-    float a = 0.f, b = 0.f, d = 0.f;
-#pragma unroll
-    for (int t = 0; t < 11; ++t) {
-      const float w = c_win[t];
-      a += w * v[0][o + t]; b += w * v[1][o + t]; d += w * v[2][o + t];
-    }
     if (x < W && y < H) {
       size_t off = pbase + (size_t)y * W + x;
       float xv = img1[off], yv = img2[off];
-      float g = sc * (a + 2.f * xv * b + yv * d);
+      float g = sc * (g12[o].x + 2.f * xv * g12[o].y + yv * g3[o]);
       if (l1_scale != 0.f) {
         float df = xv - yv;
         g += l1_scale * (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));

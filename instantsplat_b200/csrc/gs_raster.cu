@@ -399,7 +399,7 @@ struct OutPtrs {
 };
 
 __global__ void __launch_bounds__(kPT, 4)
-k_preprocess_bwd(InPtrs in, GeomView gv, const int* __restrict__ radii_unused, OutPtrs out) {
+k_preprocess_bwd(InPtrs in, GeomView gv, const int pose_only_layout, OutPtrs out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CamConst* cam = reinterpret_cast<CamConst*>(smem_raw);
   float* sm = reinterpret_cast<float*>(smem_raw + ((sizeof(CamConst) + 15) / 16) * 16);
@@ -438,6 +438,7 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int* __restrict__ radii_unused, O
   if (t < nv) {
     float4 d0 = gv.dacc[3 * (size_t)i], d1 = gv.dacc[3 * (size_t)i + 1], d2 = gv.dacc[3 * (size_t)i + 2];
     float ds[9] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x};
+    if (pose_only_layout) { ds[8] = ds[5]; ds[5] = 0.f; }     // tracking mode: dacc[5] carries dL/db, no dL/dopacity
     bool any = false;
 #pragma unroll
     for (int k = 0; k < 9; ++k) any |= (ds[k] != 0.f);
@@ -448,6 +449,20 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int* __restrict__ radii_unused, O
       project_geometry(*cam, g, in.cov3D ? in.cov3D + (size_t)6 * i : nullptr, p);
       if (p.visible) {
         p.clamped = gv.clamped[i];
+        // The blend backward accumulates RAW pixel moments of w = dL/dalpha * (opacity * G) per Gaussian
+        //   ds = [S w dx, S w dy, S w dx^2, S w dx dy, S w dy^2, S w, dL/dr, dL/dg, dL/db];
+        // the per-Gaussian constants are applied once here instead of once per (warp, Gaussian) in the blend kernel:
+        //   dL/dx = -(A Sx + B Sy), dL/dy = -(C Sy + B Sx), dL/dA = -Sxx/2, dL/dB = -Sxy, dL/dC = -Syy/2,
+        //   dL/dopacity = Sw / opacity.
+        {
+          const float sx = ds[0], sy = ds[1];
+          ds[0] = -(p.A * sx + p.B * sy);
+          ds[1] = -(p.C * sy + p.B * sx);
+          ds[2] *= -0.5f;
+          ds[3] = -ds[3];
+          ds[4] *= -0.5f;
+          ds[5] = ds[5] / p.opacity;
+        }
         project_bwd(*cam, g, p, row_rest, use_sh, in.cov3D != nullptr, ds, gg, row_dc, row_rest, pa);
         has = use_sh;
       }
@@ -659,7 +674,12 @@ extern "C" GSB_API int gsb_backward(const GsbCamera* cam, const GsbGaussians* g,
     return GSB_OK;
   }
   GSB_CUDA(cudaMemsetAsync(gv.dacc, 0, (size_t)P * 48, st));
-  rc = gsb_launch_blend_bwd(bv, iv, cam->bg, W, H, dL_dout, (float*)gv.dacc, st);
+  // tracking mode (render.py:99-170): only dL/dpose is wanted -> the blend backward reduces 8 values instead of 9
+  const bool pose_only = g->pose && grads->dL_dpose && !grads->dL_dmeans3D && !grads->dL_dmeans2D && !grads->dL_dscales &&
+                         !grads->dL_drotations && !grads->dL_dopacities && !grads->dL_dsh_dc && !grads->dL_dsh_rest &&
+                         !grads->dL_dcolors && !grads->dL_dcov3D && gsb_option_blend_version() == 2 &&
+                         gsb_option_stage_bulk() == 1;
+  rc = gsb_launch_blend_bwd(bv, iv, cam->bg, W, H, dL_dout, (float*)gv.dacc, pose_only, st);
   if (rc) return rc;
   OutPtrs out;
   out.dmeans = grads->dL_dmeans3D; out.dmeans2D = grads->dL_dmeans2D; out.dscales = grads->dL_dscales;
@@ -670,7 +690,7 @@ extern "C" GSB_API int gsb_backward(const GsbCamera* cam, const GsbGaussians* g,
   if (a & 15) in.vec_ok = 0;
   const int nb = (P + kPT - 1) / kPT;
   { ProfScope ps(GSB_K_PREPROCESS_BWD, st, g->pose ? 3 : 1);
-    k_preprocess_bwd<<<nb, kPT, kPrepSmem, st>>>(in, gv, nullptr, out);
+    k_preprocess_bwd<<<nb, kPT, kPrepSmem, st>>>(in, gv, pose_only ? 1 : 0, out);
     if (g->pose) {
       k_pose_reduce<<<16, 256, 0, st>>>(gv.pose_part, nb, gv.pose_acc);
       k_pose_finalize<<<1, 32, 0, st>>>(gv.pose_acc, g->pose, grads->dL_dpose);

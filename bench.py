@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink P (debug only; invalidates the number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--blend-version", type=int, default=0, help="debug: force blend kernel version 1|2|3")
-    ap.add_argument("--exchange", default="fused_p2p", choices=["allreduce", "fused_p2p"],
+    ap.add_argument("--exchange", default="fused_p2p", choices=["allreduce", "fused_p2p", "fused_p2p_nccl"],
                     help="multi-GPU gradient exchange: NCCL all-reduce + Adam, or the fused P2P "
                          "reduce-scatter->Adam->all-gather kernel (default)")
     return ap.parse_args()

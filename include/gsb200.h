@@ -200,6 +200,20 @@ GSB_API int gsb_ipc_open(const unsigned char* handle64, void** dev_ptr);
 GSB_API int gsb_ipc_close(void* dev_ptr);
 GSB_API int gsb_ipc_free(void* dev_ptr);
 
+/* Flag barrier / small exchange over peer memory (replace the tiny NCCL collectives around the fused kernel).
+ * peer_signal: host array of `world` device pointers to every rank's signal buffer (gsb_peer_signal_bytes() bytes,
+ * allocated zeroed with gsb_ipc_alloc, own rank included).  epoch: the optimizer step, 1, 2, 3, ... (same on all
+ * ranks).  gsb_peer_exchange (channel 0): flags8[0..6] gate flags, overflow_word (device, may be NULL) and
+ * pose_grad[n_pose] are replaced IN PLACE by their sums over the ranks (flags8[7] = number of ranks whose
+ * overflow_word was set); it is also the barrier "every rank's gradients are written".  gsb_peer_barrier: pure
+ * barrier on `channel` (use 1 after the fused kernel: "every rank's parameter stores have landed").  A wait that
+ * exceeds ~3 s sets word 60 of the local signal buffer and returns (the GPU is never hung on a dead peer). */
+GSB_API size_t gsb_peer_signal_bytes(void);
+GSB_API int gsb_peer_barrier(int32_t world, int32_t rank, void* const* peer_signal, uint32_t epoch, int32_t channel,
+                             gsb_stream_t stream);
+GSB_API int gsb_peer_exchange(int32_t world, int32_t rank, void* const* peer_signal, uint32_t epoch, uint32_t* flags8,
+                              const uint32_t* overflow_word, float* pose_grad, int32_t n_pose, gsb_stream_t stream);
+
 typedef struct GsbShardPiece { /* (one tensor's segment) intersected with (this rank's shard) */
   int64_t begin, end;          /* flat-buffer element range, multiples of 4 */
   int64_t seg_begin;           /* where the tensor's segment starts in the flat buffer */

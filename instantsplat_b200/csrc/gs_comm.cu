@@ -117,6 +117,79 @@ __global__ void __launch_bounds__(kFT) k_fused_rs_adam_ag(FusedArgs a, const uns
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Flag barriers and the small exchange (gate flags, binning-overflow word, pose-gradient table) over the same peer
+// memory -- they replace the two tiny NCCL collectives that used to bracket the fused kernel (each cost a ring
+// latency plus a launch at 8 ranks; these are one NVLink round trip).
+//
+// Signal buffer of every rank (uint32 words, peer-visible, zero-initialised):
+//   [parity 2][channel 2][world]            epoch flags   (word  p*16 + c*8 + src)
+//   word 60                                 local error word (1 = a wait timed out)
+//   [parity 2][world][kXchMax] floats       exchange slots (from word 64)
+// A rank stores its contribution into slot [parity][rank] of EVERY peer, fences, then stores the step's epoch into
+// flag [parity][channel][rank] of every peer with release semantics, and finally waits (acquire) until all `world`
+// flags in its OWN buffer carry the epoch.  Parity = epoch & 1, so a slot is rewritten only two steps later, by
+// which time every rank has passed a later barrier and therefore finished reading it.
+constexpr int kXchMax = 256;
+constexpr int kSigWords = 64 + 2 * kMaxWorld * kXchMax;
+constexpr long long kSpinLimit = 6000000000LL;     // ~3 s at 2 GHz: never hang the GPU on a dead peer
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f32(float* p, float v) {
+  asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+struct SigArgs { int world, rank; unsigned int epoch; int channel; unsigned int* sig[kMaxWorld]; };
+
+// all threads of the (single) CTA call this; returns after every rank has signalled `epoch` on `channel`
+__device__ __forceinline__ void signal_and_wait(const SigArgs& a) {
+  const int par = (int)(a.epoch & 1u);
+  __syncthreads();
+  if ((int)threadIdx.x < a.world) {
+    __threadfence_system();
+    st_release_sys(a.sig[threadIdx.x] + par * 16 + a.channel * 8 + a.rank, a.epoch);
+    const unsigned int* mine = a.sig[a.rank] + par * 16 + a.channel * 8 + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine) != a.epoch) {
+      if (clock64() - t0 > kSpinLimit) { a.sig[a.rank][60] = 1u; break; }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_peer_barrier(SigArgs a) { signal_and_wait(a); }
+
+// flags [8] uint32 (this rank's gate flags; slot 7 is overwritten with *ovf), pose_grad [n_pose] floats: every rank
+// ends up with the SUM over ranks of both, in place, accumulated in rank order (identical on all ranks).
+__global__ void __launch_bounds__(256) k_peer_exchange(SigArgs a, unsigned int* flags, const unsigned int* ovf,
+                                                       float* pose_grad, int n_pose) {
+  const int n = 8 + n_pose;
+  const int par = (int)(a.epoch & 1u);
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    float v;
+    if (t < 7) v = (float)flags[t];
+    else if (t == 7) v = ovf ? (float)(*ovf != 0u) : 0.f;
+    else v = pose_grad[t - 8];
+    for (int p = 0; p < a.world; ++p)
+      st_relaxed_sys_f32(reinterpret_cast<float*>(a.sig[p] + 64) + ((size_t)par * kMaxWorld + a.rank) * kXchMax + t, v);
+  }
+  signal_and_wait(a);
+  const float* mine = reinterpret_cast<const float*>(a.sig[a.rank] + 64) + (size_t)par * kMaxWorld * kXchMax;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < a.world; ++p) s += *((volatile const float*)(mine + (size_t)p * kXchMax + t));
+    if (t < 8) flags[t] = (unsigned int)(s + 0.5f);
+    else pose_grad[t - 8] = s;
+  }
+}
+
 int fail(cudaError_t e, const char* what) {
   char buf[256];
   snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
@@ -215,4 +288,45 @@ extern "C" GSB_API int gsb_fused_rs_adam_ag(int32_t world, int32_t rank, const f
   gsb_prof_end(slot, st);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? GSB_OK : fail(e, "k_fused_rs_adam_ag");
+}
+
+static int make_sig(int32_t world, int32_t rank, void* const* sig, uint32_t epoch, int channel, SigArgs& a) {
+  if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || !sig || channel < 0 || channel > 1 || epoch == 0) {
+    gsb_set_error("gsb_peer_*: bad argument");
+    return GSB_ERR_INVALID;
+  }
+  a.world = world; a.rank = rank; a.epoch = epoch; a.channel = channel;
+  for (int r = 0; r < kMaxWorld; ++r) a.sig[r] = r < world ? (unsigned int*)sig[r] : nullptr;
+  for (int r = 0; r < world; ++r)
+    if (!a.sig[r]) { gsb_set_error("gsb_peer_*: null signal buffer"); return GSB_ERR_INVALID; }
+  return GSB_OK;
+}
+
+extern "C" GSB_API size_t gsb_peer_signal_bytes(void) { return (size_t)kSigWords * 4; }
+
+extern "C" GSB_API int gsb_peer_barrier(int32_t world, int32_t rank, void* const* peer_signal, uint32_t epoch,
+                                        int32_t channel, gsb_stream_t stream_) {
+  SigArgs a;
+  int rc = make_sig(world, rank, peer_signal, epoch, channel, a);
+  if (rc) return rc;
+  gsb_count_launch(1);
+  k_peer_barrier<<<1, 32, 0, (cudaStream_t)stream_>>>(a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSB_OK : fail(e, "k_peer_barrier");
+}
+
+extern "C" GSB_API int gsb_peer_exchange(int32_t world, int32_t rank, void* const* peer_signal, uint32_t epoch,
+                                         uint32_t* flags8, const uint32_t* overflow_word, float* pose_grad,
+                                         int32_t n_pose, gsb_stream_t stream_) {
+  SigArgs a;
+  int rc = make_sig(world, rank, peer_signal, epoch, 0, a);
+  if (rc) return rc;
+  if (!flags8 || n_pose < 0 || 8 + n_pose > kXchMax || (n_pose > 0 && !pose_grad)) {
+    gsb_set_error("gsb_peer_exchange: bad argument (at most 248 pose-gradient floats)");
+    return GSB_ERR_INVALID;
+  }
+  gsb_count_launch(1);
+  k_peer_exchange<<<1, 256, 0, (cudaStream_t)stream_>>>(a, flags8, overflow_word, pose_grad, n_pose);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GSB_OK : fail(e, "k_peer_exchange");
 }

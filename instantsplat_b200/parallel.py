@@ -99,6 +99,23 @@ class PeerBuffer:
         import ctypes
         return (ctypes.c_void_p * self.world)(*self.ptrs)
 
+    def close(self, group=None):
+        """Collective: drop the torch view, close the peer mappings, then (after a barrier, so that nobody still maps
+        it) free the local allocation.  The buffer must not be used afterwards."""
+        import torch.distributed as dist
+        if self.local_ptr is None:
+            return
+        torch.cuda.synchronize()
+        self.tensor = None
+        self._mem = None
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank and p:
+                self.L.gsb_ipc_close(p)
+        if dist.is_initialized():
+            dist.barrier(group=group)
+        self.L.gsb_ipc_free(self.local_ptr)
+        self.local_ptr, self.ptrs = None, []
+
 
 def shard_bounds(total: int, world: int, rank: int, align: int = 768):
     """Contiguous shard [lo, hi) of a flat buffer of `total` floats; boundaries are multiples of `align`

@@ -69,6 +69,10 @@ class OptimConfig:
     max_sh_degree = 3
 
 
+def L_sig_words():
+    return (_lib.lib().gsb_peer_signal_bytes() + 3) // 4
+
+
 def _align(n, a=64):
     return (n + a - 1) // a * a
 
@@ -80,9 +84,12 @@ class JointTrainer:
         self.cfg = cfg or OptimConfig()
         self.dev = torch.device(device)
         self.world_size, self.rank, self.pg = world_size, rank, process_group
-        if exchange not in ("allreduce", "fused_p2p"):
+        if exchange not in ("allreduce", "fused_p2p", "fused_p2p_nccl"):
             raise ValueError(f"unknown exchange mode {exchange!r}")
         self.exchange = exchange if world_size > 1 else "allreduce"
+        # fused_p2p: peer-memory kernel bracketed by flag barriers over the same peer memory (default);
+        # fused_p2p_nccl: same kernel bracketed by two tiny NCCL collectives (round-1 behaviour, kept for A/B runs)
+        self._fused = self.exchange in ("fused_p2p", "fused_p2p_nccl")
         self.P = P = scene.P
         self.W, self.H = scene.width, scene.height
         self.sh_degree = scene.sh_degree
@@ -93,7 +100,7 @@ class JointTrainer:
             offs[name] = total
             total += _align(P * k)
         self.offs, self.total = offs, total
-        if self.exchange == "fused_p2p":
+        if self._fused:
             # peer-visible parameter / gradient buffers (CUDA IPC) and shard-sized Adam moments
             from .parallel import PeerBuffer, shard_bounds
             self._peer_params = PeerBuffer(total, self.dev, process_group)
@@ -105,6 +112,9 @@ class JointTrainer:
             self.exp_avg_sq = torch.zeros(n_sh, dtype=torch.float32, device=self.dev)
             self._sync = torch.zeros(1, dtype=torch.float32, device=self.dev)
             self._xch = torch.zeros(8 + scene.n_views * 7, dtype=torch.float32, device=self.dev)
+            self._epoch = 0
+            if self.exchange == "fused_p2p":
+                self._peer_sig = PeerBuffer(L_sig_words(), self.dev, process_group)
         else:
             self.params = torch.zeros(total, dtype=torch.float32, device=self.dev)
             self.grads = torch.zeros(total, dtype=torch.float32, device=self.dev)
@@ -113,8 +123,11 @@ class JointTrainer:
         for name, k in SEGMENTS:
             self.view(self.params, name).copy_(scene.params[name].reshape(P, k).to(self.dev))
         self.poses = scene.poses.to(self.dev).float().contiguous()              # [n_views,7]
-        if self.exchange == "fused_p2p":
+        if self.exchange == "fused_p2p_nccl":
             self.pose_grad = self._xch[8:].view(scene.n_views, 7)
+            self._pg_buf = None
+        elif self.exchange == "fused_p2p":
+            self.pose_grad = torch.zeros_like(self.poses)
             self._pg_buf = None
         else:
             # [n_views*7] pose gradients + 1 word carrying this rank's binning-overflow flag through the all-reduce
@@ -158,7 +171,7 @@ class JointTrainer:
         self.flags = torch.zeros(8, dtype=torch.int32, device=self.dev)
         self._pose_flags = torch.zeros(8, dtype=torch.int32, device=self.dev)
         if world_size > 1:    # the word the optimizer kernels test: overflow flags summed over the ranks
-            self._ovf = self.flags[7:8] if self.exchange == "fused_p2p" else self._pg_buf[-1:]
+            self._ovf = self.flags[7:8] if self._fused else self._pg_buf[-1:]
         self.iteration = 0            # reference iterations = views consumed (by all ranks)
         self.opt_step = 0
         self.last_R = 0
@@ -346,12 +359,20 @@ class JointTrainer:
             a.numel, a.row_len, a.grad_scale = g.numel(), k, 1.0
             a.step_size, a.beta1, a.beta2, a.eps, a.weight_decay = 0.0, b1, b2, eps, 0.0
         check(L.gsb_adam_gate(len(SEGMENTS), arr, self.flags.data_ptr(), st), "gsb_adam_gate")
-        # one small SUM all-reduce carries both the gate flags (as counts) and the pose-gradient table
-        # (self.pose_grad is a view of self._xch[8:]); it is also the pre-barrier of the fused kernel
-        self._xch[:8].copy_(self.flags)
-        self._xch[7:8].copy_(self._status_t[1:2])          # slot 7: binning overflow (summed over ranks)
-        dist.all_reduce(self._xch, op=dist.ReduceOp.SUM, group=self.pg)
-        self.flags.copy_(self._xch[:8])
+        if self.exchange == "fused_p2p":
+            # gate flags, the binning-overflow word and the pose-gradient table are summed over the ranks by ONE tiny
+            # kernel through peer memory; its flag barrier is also "every rank's gradients are written"
+            self._epoch += 1
+            check(L.gsb_peer_exchange(self.world_size, self.rank, self._peer_sig.ptr_array(), self._epoch,
+                                      self.flags.data_ptr(), self._status_dev + 4, self.pose_grad.data_ptr(),
+                                      self.pose_grad.numel(), st), "gsb_peer_exchange")
+        else:
+            # one small SUM all-reduce carries both the gate flags (as counts) and the pose-gradient table
+            # (self.pose_grad is a view of self._xch[8:]); it is also the pre-barrier of the fused kernel
+            self._xch[:8].copy_(self.flags)
+            self._xch[7:8].copy_(self._status_t[1:2])          # slot 7: binning overflow (summed over ranks)
+            dist.all_reduce(self._xch, op=dist.ReduceOp.SUM, group=self.pg)
+            self.flags.copy_(self._xch[:8])
         # 2. the fused kernel over this rank's shard
         lo, hi = self.shard
         pieces = []
@@ -378,18 +399,40 @@ class JointTrainer:
                               beta1=b1, beta2=b2, eps=eps, weight_decay=0.0, grad_scale=1.0 / self.world_size)],
                         self._pose_flags, skip_ptr=self._ovf.data_ptr())
         # 4. nobody may start the next forward before every rank's parameter stores have landed
-        dist.all_reduce(self._sync, group=self.pg)
+        if self.exchange == "fused_p2p":
+            check(L.gsb_peer_barrier(self.world_size, self.rank, self._peer_sig.ptr_array(), self._epoch, 1, st),
+                  "gsb_peer_barrier")
+        else:
+            dist.all_reduce(self._sync, group=self.pg)
 
     def _run_iteration(self, view: int, gt: torch.Tensor, do_opt: bool) -> None:
         self._launch_forward(view)
         self.loss_and_backward(view, gt)
         if not do_opt:
             return
-        if self.exchange == "fused_p2p":
+        if self._fused:
             self.fused_exchange_step()
         else:
             self.reduce_grads()
             self.optimizer_step()
+
+    def close(self) -> None:
+        """Release the peer-visible buffers of the fused exchange (collective over the process group)."""
+        for name in ("_peer_params", "_peer_grads", "_peer_sig"):
+            pb = getattr(self, name, None)
+            if pb is not None:
+                if name == "_peer_params":
+                    self.params = None
+                if name == "_peer_grads":
+                    self.grads = None
+                pb.close(self.pg)
+                setattr(self, name, None)
+
+    def check_peer_errors(self) -> None:
+        """Raise if a flag-barrier wait timed out on this rank (a peer died or fell out of step)."""
+        if getattr(self, "_peer_sig", None) is not None:
+            if int(self._peer_sig.tensor[60:61].view(torch.int32).item()) != 0:
+                raise _lib.GsbError(f"rank {self.rank}: a peer flag barrier timed out")
 
     def step(self, view: int, gt: Optional[torch.Tensor] = None) -> None:
         """One reference iteration on `view` (train.py:140-211): update_learning_rate(iteration), oneupSHdegree every
@@ -426,7 +469,7 @@ class JointTrainer:
     # optimizer's step counter is untouched by all three, as in the reference (state["step"] survives the surgery).
     def _resize(self, new_P: int, rows) -> None:
         """rows(name, old_param_view, old_m_view, old_v_view) -> (param, m, v) tensors of shape [new_P, k]."""
-        if self.exchange == "fused_p2p":
+        if self._fused:
             raise _lib.GsbError("changing the number of Gaussians is not supported with peer-memory buffers "
                                 "(exchange='fused_p2p'); use exchange='allreduce'")
         L = _lib.lib()

@@ -1,5 +1,10 @@
-"""torchrun worker for tests/test_multigpu.py: a 2-GPU view-sharded optimizer step must equal a
-single-GPU step on the gradients accumulated over the same two views."""
+"""torchrun worker for tests/test_multigpu.py: a view-sharded optimizer step on G GPUs must equal -- BIT FOR BIT -- a
+single-GPU Adam step on the per-rank gradients summed in rank order.
+
+The blend backward accumulates with floating-point atomics, so re-rendering a view reproduces its gradient only up
+to the last bits (and Adam turns a last-bit difference of a near-zero gradient into a full step of either sign).  The
+comparison therefore uses the gradients each rank ACTUALLY produced (captured before the exchange and gathered on
+rank 0): with them the expected parameters are fully determined and no outlier allowance is needed."""
 import os
 import sys
 
@@ -16,39 +21,60 @@ dev = torch.device("cuda", local)
 sc = surface_scene(20_000, 4, 256, 192, seed=9, sh_degree=3)
 gts = torch.rand(4, 3, sc.height, sc.width, generator=torch.Generator().manual_seed(2))
 mode = os.environ.get("GSB_TEST_MODE", "allreduce")
+N_STEPS = 3
 tr = I.JointTrainer(sc, dev, gt_images=gts, world_size=world, rank=rank, exchange=mode)
-for s in range(2):
-    tr.step(view_for_step(sc.n_views, world, rank, s))
+captured = []
+for s in range(N_STEPS):
+    v = view_for_step(sc.n_views, world, rank, s)
+    tr.iteration += world
+    tr._launch_forward(v)
+    tr.loss_and_backward(v, tr.gt[v])
+    captured.append((tr.grads.clone(), tr.pose_grad.clone()))
+    if tr._fused:
+        tr.fused_exchange_step()
+    else:
+        tr.reduce_grads()
+        tr.optimizer_step()
+    assert tr._settle()
 torch.cuda.synchronize()
+tr.check_peer_errors()
 # every replica must hold identical parameters
 mine = tr.params.clone()
 ref0 = mine.clone()
 dist.broadcast(ref0, src=0)
 assert torch.equal(mine, ref0), f"rank {rank}: replicas diverged"
+poses0 = tr.poses.clone()
+dist.broadcast(poses0, src=0)
+assert torch.equal(tr.poses, poses0), f"rank {rank}: pose tables diverged"
+# gather the per-rank gradients of every step on rank 0
+gathered = []
+for g, pg in captured:
+    gl = [torch.empty_like(g) for _ in range(world)]
+    pl = [torch.empty_like(pg) for _ in range(world)]
+    dist.all_gather(gl, g.contiguous())
+    dist.all_gather(pl, pg.contiguous())
+    gathered.append((gl, pl))
 if rank == 0:
     one = I.JointTrainer(sc, dev, gt_images=gts)
-    for s in range(2):
-        acc = torch.zeros_like(one.grads)
-        pacc = torch.zeros_like(one.pose_grad)
-        for r in range(world):
-            v = view_for_step(sc.n_views, world, r, s)
-            one.render(v)
-            one.loss_and_backward(v, one.gt[v])
-            acc += one.grads
-            pacc += one.pose_grad
+    for s, (gl, pl) in enumerate(gathered):
+        acc, pacc = gl[0].clone(), pl[0].clone()
+        for r in range(1, world):
+            acc += gl[r]
+            pacc += pl[r]
         one.grads.copy_(acc)
         one.pose_grad.copy_(pacc)
-        one.iteration += 1
+        one.iteration += world
         one.optimizer_step(grad_scale=1.0 / world)
     torch.cuda.synchronize()
-    # The blend backward accumulates with floating-point atomics, so two runs of the same view differ in the
-    # last bits of the gradients.  Adam turns a gradient whose true value is ~0 (below that noise) into a
-    # full-size step of random sign, so a handful of parameters may legitimately differ; everything else must
-    # agree to rounding.
-    diff = (one.params - mine).abs()
-    frac_bad = float((diff > 2e-6).float().mean())
+    diff = float((one.params - mine).abs().max())
     perr = float((one.poses - tr.poses).abs().max())
-    assert frac_bad < 2e-4 and perr < 1e-6, (frac_bad, float(diff.max()), perr)
-    print(f"MGPU_OK mode={mode} outlier fraction {frac_bad:.2e} (max diff {float(diff.max()):.2e}) pose diff {perr:.2e}")
+    # NCCL may add in a different order for more than two ranks; the fused kernel adds in rank order for any world
+    tol = 0.0 if (tr._fused or world == 2) else 1e-6
+    assert diff <= tol and perr <= tol, (mode, diff, perr)
+    # the step must actually have moved the parameters
+    moved = float((one.view(one.params, "xyz") - sc.params["xyz"].to(dev)).abs().max())
+    assert moved > 0
+    print(f"MGPU_OK mode={mode} world={world} steps={N_STEPS} max param diff {diff:.1e} pose diff {perr:.1e}")
 dist.barrier()
+tr.close()
 dist.destroy_process_group()

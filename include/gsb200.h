@@ -106,8 +106,8 @@ GSB_API size_t gsb_image_bytes(int32_t width, int32_t height);
 
 /* Forward, phase 1: per-Gaussian projection (+ fused pose / activations / SH->RGB), lossless tile culling,
  * instance counts per Gaussian and per tile, tile-segment offsets.  Writes radii [P] (int32).  The number of
- * (Gaussian, tile) instances R stays on the device; if status_host != NULL (pinned host memory, 4 words) the
- * status words {R, 0, longest tile list, 0} are copied there asynchronously (valid once the stream reaches
+ * (Gaussian, tile) instances R stays on the device; if status_host != NULL (pinned host memory, 8 words) the
+ * status words {R, 0, longest tile list, 0, long lists, very long lists, forward serial number, -} are copied there asynchronously (valid once the stream reaches
  * this point) -- a caller that wants an exactly-sized binning buffer waits for it, nobody else has to. */
 GSB_API int gsb_preprocess(const GsbCamera* cam, const GsbGaussians* g, void* geom, size_t geom_bytes,
                    int32_t* radii, uint32_t* status_host, gsb_stream_t stream);
@@ -116,8 +116,8 @@ GSB_API int gsb_preprocess(const GsbCamera* cam, const GsbGaussians* g, void* ge
  * gather) and the per-tile blend.  R is the instance CAPACITY the binning buffer was sized for
  * (gsb_binning_bytes(R, w, h) <= binning_bytes); it need not be the exact count.  If the true count exceeds
  * it the tile lists are truncated (memory-safe, image approximate) and status word 1 (overflow) is set.
- * status_host (optional, pinned, 4 words): {R true, overflow, longest list, tiles sorted by the slow global
- * path}, copied asynchronously after the blend has been enqueued.  out_color [3,H,W]. */
+ * status_host (optional, pinned, 8 words): {R true, overflow, longest list, tiles sorted by the slow global
+ * path, #lists > 2048, #lists > 8192, forward serial number, -}, copied asynchronously after the blend has been enqueued.  out_color [3,H,W]. */
 GSB_API int gsb_render(const GsbCamera* cam, int32_t P, void* geom, void* binning, size_t binning_bytes,
                int64_t R, void* image, float* out_color, uint32_t* status_host, gsb_stream_t stream);
 
@@ -213,6 +213,12 @@ GSB_API int gsb_peer_barrier(int32_t world, int32_t rank, void* const* peer_sign
                              gsb_stream_t stream);
 GSB_API int gsb_peer_exchange(int32_t world, int32_t rank, void* const* peer_signal, uint32_t epoch, uint32_t* flags8,
                               const uint32_t* overflow_word, float* pose_grad, int32_t n_pose, gsb_stream_t stream);
+
+/* Same again, with the per-tensor step sizes read from a DEVICE array (float[n], step_sizes_dev[k] replaces
+ * tensors_host[k].step_size) when it is not NULL: the launch can then sit in a CUDA graph and be replayed while the
+ * host refreshes the array (learning-rate schedule, bias correction) before every replay. */
+GSB_API int gsb_adam_step_ex(int32_t n, const GsbAdamTensor* tensors_host, uint32_t* flags,
+                             const uint32_t* skip_if_nonzero, const float* step_sizes_dev, gsb_stream_t stream);
 
 typedef struct GsbShardPiece { /* (one tensor's segment) intersected with (this rank's shard) */
   int64_t begin, end;          /* flat-buffer element range, multiples of 4 */

@@ -63,7 +63,7 @@ EXPORTS = ("gsb_geom_bytes", "gsb_binning_bytes", "gsb_image_bytes", "gsb_prepro
            "gsb_loss_forward", "gsb_loss_backward", "gsb_adam_step", "gsb_last_error",
            "gsb_abi_version", "gsb_profile_enable", "gsb_profile_collect", "gsb_launch_count", "gsb_set_option", "gsb_adam_gate",
            "gsb_ipc_alloc", "gsb_ipc_open", "gsb_ipc_close", "gsb_ipc_free", "gsb_fused_rs_adam_ag",
-           "gsb_knn_scratch_bytes", "gsb_knn_mean_dist2", "gsb_status_device", "gsb_adam_step_gated", "gsb_blend_stats", "gsb_l1_mask_fwd_bwd", "gsb_track_step", "gsb_peer_signal_bytes", "gsb_peer_barrier", "gsb_peer_exchange")
+           "gsb_knn_scratch_bytes", "gsb_knn_mean_dist2", "gsb_status_device", "gsb_adam_step_gated", "gsb_blend_stats", "gsb_l1_mask_fwd_bwd", "gsb_track_step", "gsb_peer_signal_bytes", "gsb_peer_barrier", "gsb_peer_exchange", "gsb_adam_step_ex")
 KERNEL_IDS = ("preprocess", "sort_depth", "scan", "duplicate", "sort_tile", "gather", "blend_fwd", "blend_bwd",
               "preprocess_bwd", "loss_fwd", "loss_bwd", "adam")
 
@@ -113,6 +113,8 @@ def lib() -> ctypes.CDLL:
     L.gsb_peer_barrier.restype = ctypes.c_int
     L.gsb_peer_exchange.argtypes = [i32, i32, ctypes.POINTER(vp), ctypes.c_uint32, vp, vp, vp, i32, vp]
     L.gsb_peer_exchange.restype = ctypes.c_int
+    L.gsb_adam_step_ex.argtypes = [i32, ctypes.POINTER(GsbAdamTensor), vp, vp, vp, vp]
+    L.gsb_adam_step_ex.restype = ctypes.c_int
     L.gsb_status_device.argtypes = [vp, i32]
     L.gsb_status_device.restype = vp
     L.gsb_adam_step_gated.argtypes = [i32, ctypes.POINTER(GsbAdamTensor), vp, vp, vp]

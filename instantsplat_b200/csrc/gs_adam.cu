@@ -27,7 +27,7 @@ struct AdamT {
   float step, b1, omb1, b2, omb2, eps, wd, gscale;
   unsigned int first_block, nblocks;
 };
-struct AdamArgs { int n; AdamT t[GSB_ADAM_MAX_TENSORS]; };
+struct AdamArgs { int n; const float* step_dev; AdamT t[GSB_ADAM_MAX_TENSORS]; };
 
 constexpr int kAT = 256;
 constexpr int kPerThread = 8;                     // 2 x float4
@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(kAT) k_adam_gate(AdamArgs a, unsigned int* fla
   }
 }
 
-__device__ __forceinline__ void adam_elem(const AdamT& t, bool gate, float lr_mul, float& p, float g, float& m,
-                                          float& v) {
+__device__ __forceinline__ void adam_elem(const AdamT& t, float step, bool gate, float lr_mul, float& p, float g,
+                                          float& m, float& v) {
   g *= t.gscale;
   if (t.wd != 0.f) g = __fmaf_rn(t.wd, p, g);
   if (gate) {
@@ -86,7 +86,7 @@ __device__ __forceinline__ void adam_elem(const AdamT& t, bool gate, float lr_mu
   }
   float denom = __fadd_rn(__fsqrt_rn(v), t.eps);
   float upd = __fdiv_rn(m, denom);
-  p = __fadd_rn(p, __fmul_rn(-(t.step * lr_mul), upd));
+  p = __fadd_rn(p, __fmul_rn(-(step * lr_mul), upd));
 }
 
 __global__ void __launch_bounds__(kAT) k_adam(AdamArgs a, const unsigned int* __restrict__ flags,
@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(kAT) k_adam(AdamArgs a, const unsigned int* __
   const int k = find_tensor(a, blockIdx.x);
   const AdamT& t = a.t[k];
   const bool gate = flags[k] != 0;
+  // step size = lr * sqrt(1-b2^t)/(1-b1^t): a launch argument, or (CUDA-graph replay: arguments are frozen) read from
+  // a device array the host refreshes before every replay
+  const float step = a.step_dev ? a.step_dev[k] : t.step;
   const long long base = (long long)(blockIdx.x - t.first_block) * kPerBlock;
   const bool vec = ((((uintptr_t)t.p | (uintptr_t)t.g | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0);
   if (vec && base + kPerBlock <= t.numel) {
@@ -110,10 +113,10 @@ __global__ void __launch_bounds__(kAT) k_adam(AdamArgs a, const unsigned int* __
         l0 = __ldg(t.ppl + e / t.row_len); l1 = __ldg(t.ppl + (e + 1) / t.row_len);
         l2 = __ldg(t.ppl + (e + 2) / t.row_len); l3 = __ldg(t.ppl + (e + 3) / t.row_len);
       }
-      adam_elem(t, gate, l0, p.x, g.x, m.x, v.x);
-      adam_elem(t, gate, l1, p.y, g.y, m.y, v.y);
-      adam_elem(t, gate, l2, p.z, g.z, m.z, v.z);
-      adam_elem(t, gate, l3, p.w, g.w, m.w, v.w);
+      adam_elem(t, step, gate, l0, p.x, g.x, m.x, v.x);
+      adam_elem(t, step, gate, l1, p.y, g.y, m.y, v.y);
+      adam_elem(t, step, gate, l2, p.z, g.z, m.z, v.z);
+      adam_elem(t, step, gate, l3, p.w, g.w, m.w, v.w);
       *reinterpret_cast<float4*>(t.p + e) = p;
       *reinterpret_cast<float4*>(t.m + e) = m;
       *reinterpret_cast<float4*>(t.v + e) = v;
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(kAT) k_adam(AdamArgs a, const unsigned int* __
       if (e < t.numel) {
         float p = t.p[e], m = t.m[e], v = t.v[e];
         float l = t.ppl ? t.ppl[e / t.row_len] : 1.f;
-        adam_elem(t, gate, l, p, t.g[e], m, v);
+        adam_elem(t, step, gate, l, p, t.g[e], m, v);
         t.p[e] = p; t.m[e] = m; t.v[e] = v;
       }
     }
@@ -135,6 +138,7 @@ __global__ void __launch_bounds__(kAT) k_adam(AdamArgs a, const unsigned int* __
 
 static int build_args(int32_t n, const GsbAdamTensor* ts, AdamArgs& a, unsigned int& nb) {
   a.n = n;
+  a.step_dev = nullptr;
   nb = 0;
   for (int i = 0; i < n; ++i) {
     const GsbAdamTensor& s = ts[i];
@@ -185,8 +189,9 @@ extern "C" GSB_API int gsb_adam_gate(int32_t n, const GsbAdamTensor* ts, uint32_
   return finish(e, "gsb_adam_gate");
 }
 
-extern "C" GSB_API int gsb_adam_step_gated(int32_t n, const GsbAdamTensor* ts, uint32_t* flags,
-                                           const uint32_t* skip_if_nonzero, gsb_stream_t stream_) {
+extern "C" GSB_API int gsb_adam_step_ex(int32_t n, const GsbAdamTensor* ts, uint32_t* flags,
+                                        const uint32_t* skip_if_nonzero, const float* step_sizes_dev,
+                                        gsb_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (n < 0 || n > GSB_ADAM_MAX_TENSORS || (n > 0 && (!ts || !flags))) {
     gsb_set_error("gsb_adam_step: bad argument");
@@ -197,6 +202,7 @@ extern "C" GSB_API int gsb_adam_step_gated(int32_t n, const GsbAdamTensor* ts, u
   unsigned int nb;
   int rc = build_args(n, ts, a, nb);
   if (rc) return rc;
+  a.step_dev = step_sizes_dev;
   cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, st);
   if (e == cudaSuccess && nb > 0) {
     gsb_count_launch(2);
@@ -209,6 +215,11 @@ extern "C" GSB_API int gsb_adam_step_gated(int32_t n, const GsbAdamTensor* ts, u
   return finish(e, "gsb_adam_step");
 }
 
+extern "C" GSB_API int gsb_adam_step_gated(int32_t n, const GsbAdamTensor* ts, uint32_t* flags,
+                                           const uint32_t* skip_if_nonzero, gsb_stream_t stream) {
+  return gsb_adam_step_ex(n, ts, flags, skip_if_nonzero, nullptr, stream);
+}
+
 extern "C" GSB_API int gsb_adam_step(int32_t n, const GsbAdamTensor* ts, uint32_t* flags, gsb_stream_t stream) {
-  return gsb_adam_step_gated(n, ts, flags, nullptr, stream);
+  return gsb_adam_step_ex(n, ts, flags, nullptr, nullptr, stream);
 }

@@ -83,6 +83,11 @@ __global__ void __launch_bounds__(kScanT) k_tile_scan(GeomView gv, int ntiles) {
     gv.status[kStHugeTiles] = 0u;
     gv.status[kStNLarge] = s_nq[0];
     gv.status[kStNHuge] = s_nq[1];
+    // forward serial number: lets a host that replays this launch from a CUDA graph recognise, in the status words it
+    // receives in pinned memory, which forward they belong to (word 7 is the device-resident counter)
+    const uint32_t seq = gv.status[7] + 1u;
+    gv.status[7] = seq;
+    gv.status[kStSeq] = seq;
   }
 }
 

@@ -441,13 +441,14 @@ k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
     if (!(wdoneA && wdoneB)) {
       for (int b = 0; b < cnt; b += 32) {
         const int j = b + lane;
-        bool hitA = false, hitB = false;
+        // ONE conservative cull test per entry: the bounding rectangle of the halves that are still live (while both
+        // are, the 8x8 block -- a superset of the two 8x4 tests; extra pairs fail the exact per-pixel test)
+        bool hit = false;
         if (j < cnt) {
           const float4 e0 = sm0[j], e1 = sm1[j];
-          if (!wdoneA) hitA = slab_may_contribute(e0, e1, rx0, ryA0, rx1, ryA1);
-          if (!wdoneB) hitB = slab_may_contribute(e0, e1, rx0, ryB0, rx1, ryB1);
+          hit = slab_may_contribute(e0, e1, rx0, wdoneA ? ryB0 : ryA0, rx1, wdoneB ? ryA1 : ryB1);
         }
-        unsigned mask = __ballot_sync(0xffffffffu, hitA || hitB);
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
         while (mask) {
           const int k = __ffs(mask) - 1;
           mask &= mask - 1;
@@ -582,8 +583,8 @@ k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
         bool hit = false;
         if (j < cnt) {
           const float4 e0 = sm0[j], e1 = sm1[j];
-          if (base + j < wmaxA) hit = slab_may_contribute(e0, e1, rx0, ryA0, rx1, ryA1);
-          if (!hit && base + j < wmaxB) hit = slab_may_contribute(e0, e1, rx0, ryB0, rx1, ryB1);
+          const bool la = base + j < wmaxA, lb = base + j < wmaxB;        // which halves can still contain contributors
+          if (la || lb) hit = slab_may_contribute(e0, e1, rx0, la ? ryA0 : ryB0, rx1, lb ? ryB1 : ryA1);
         }
         unsigned mask = __ballot_sync(0xffffffffu, hit);
         while (mask) {

@@ -52,7 +52,8 @@ constexpr int kPT = 128;           // threads (= Gaussians) per CTA in the per-G
 constexpr int kMaxTiles = 65536;   // tile ids are 16 bit (a 4K frame has 32400 tiles)
 
 // status words written by the forward (device) and copied to the caller's pinned host array
-enum { kStR = 0, kStOverflow = 1, kStMaxList = 2, kStHugeTiles = 3, kStNLarge = 4, kStNHuge = 5, kStWords = 8 };
+enum { kStR = 0, kStOverflow = 1, kStMaxList = 2, kStHugeTiles = 3, kStNLarge = 4, kStNHuge = 5, kStSeq = 6,
+       kStWords = 8 };
 // tile-list size classes of the per-tile sort (gs_bin.cu): <= kSmallList entries are sorted by the one-CTA-per-tile
 // kernel; longer lists are queued by k_tile_scan and drained by two persistent kernels
 constexpr uint32_t kSmallList = 2048, kLargeList = 8192;

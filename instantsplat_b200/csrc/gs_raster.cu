@@ -631,7 +631,7 @@ extern "C" GSB_API int gsb_preprocess(const GsbCamera* cam, const GsbGaussians* 
   }
   rc = gsb_launch_tile_scan(gv, ntiles, st);
   if (rc) return rc;
-  if (status_host) GSB_CUDA(cudaMemcpyAsync(status_host, gv.status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (status_host) GSB_CUDA(cudaMemcpyAsync(status_host, gv.status, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   GSB_CUDA(cudaGetLastError());
   return GSB_OK;
 }
@@ -650,7 +650,7 @@ extern "C" GSB_API int gsb_render(const GsbCamera* cam, int32_t P, void* geom, v
   if (rc) return rc;
   rc = gsb_launch_blend_fwd(bv, iv, cam->bg, W, H, out_color, st);
   if (rc) return rc;
-  if (status_host) GSB_CUDA(cudaMemcpyAsync(status_host, gv.status, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (status_host) GSB_CUDA(cudaMemcpyAsync(status_host, gv.status, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   GSB_CUDA(cudaGetLastError());
   return GSB_OK;
 }

@@ -50,10 +50,10 @@ _pending = {}           # same key -> _State whose capacity check has not been r
 
 
 class _StatusRing:
-    """Pinned 4-word status slots, recycled round-robin (a slot is long verified before it comes round again)."""
+    """Pinned 8-word status slots, recycled round-robin (a slot is long verified before it comes round again)."""
 
     def __init__(self, n=512):
-        self.buf = torch.zeros(n, 4, dtype=torch.int32).pin_memory()
+        self.buf = torch.zeros(n, 8, dtype=torch.int32).pin_memory()
         self.n, self.i = n, 0
 
     def take(self) -> torch.Tensor:
@@ -100,12 +100,8 @@ def _render_phase(st: _State, cap: int, dev):
     bin_bytes = (L.gsb_binning_bytes(cap, W, H) + (1 << 25) - 1) >> 25 << 25
     st.binning = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
     st.bin_bytes, st.R = bin_bytes, cap
-    st.status = _status_slot()
     check(L.gsb_render(ctypes.byref(st.cam), st.P, st.geom.data_ptr(), st.binning.data_ptr(), bin_bytes, cap,
-                       st.image.data_ptr(), st.color.data_ptr(), st.status.data_ptr(), _lib.stream_ptr()),
-          "gsb_render")
-    st.event = torch.cuda.Event()
-    st.event.record()
+                       st.image.data_ptr(), st.color.data_ptr(), None, _lib.stream_ptr()), "gsb_render")
     st.checked = False
 
 
@@ -119,8 +115,9 @@ def _verify(st: _State, dev) -> None:
     phase in place with an exactly sized one (image and scratch become exact before anybody differentiates)."""
     if st.checked:
         return
-    st.event.synchronize()
-    R_true, overflow = int(st.status[0]) & 0xFFFFFFFF, int(st.status[1])
+    st.event.synchronize()                 # recorded right behind the tile scan: early in the forward
+    R_true = int(st.status[0]) & 0xFFFFFFFF
+    overflow = R_true > st.R
     _note_R(st.key, R_true)
     st.checked, st.R_true = True, R_true
     _pending.pop(st.key, None)
@@ -129,7 +126,6 @@ def _verify(st: _State, dev) -> None:
                       "the render phase was repeated with an exact buffer", RuntimeWarning)
         with torch.cuda.device(dev):
             _render_phase(st, R_true, dev)
-            st.event.synchronize()
             st.checked = True
 
 
@@ -147,7 +143,7 @@ def _verify_pending(key, dev) -> None:
         return
     event.synchronize()
     _note_R(key, int(status[0]) & 0xFFFFFFFF)
-    if int(status[1]):
+    if (int(status[0]) & 0xFFFFFFFF) > cap:
         warnings.warn(f"instantsplat_b200: a forward-only call rendered with a truncated binning buffer "
                       f"({_last_R[key]} instances > capacity {cap}); the capacity has been raised", RuntimeWarning)
 
@@ -182,15 +178,15 @@ def _forward(settings, means3D, scales, rotations, opacities, sh_dc, sh_rest, sh
         st.image = torch.empty(L.gsb_image_bytes(W, H), dtype=torch.uint8, device=dev)
         st.color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
         est = _last_R.get(st.key) if (SYNC_FREE and not settings.debug) else None
+        st.status = _status_slot()
+        check(L.gsb_preprocess(ctypes.byref(st.cam), ctypes.byref(g), st.geom.data_ptr(), geom_bytes,
+                               radii.data_ptr(), st.status.data_ptr(), stream), "gsb_preprocess")
+        st.event = torch.cuda.Event()
+        st.event.record()
         if est is None:
-            host = _status_slot()
-            check(L.gsb_preprocess(ctypes.byref(st.cam), ctypes.byref(g), st.geom.data_ptr(), geom_bytes,
-                                   radii.data_ptr(), host.data_ptr(), stream), "gsb_preprocess")
-            torch.cuda.current_stream().synchronize()      # exact sizing: wait for R once
-            cap = int(host[0]) & 0xFFFFFFFF
+            st.event.synchronize()                         # exact sizing: wait for R once
+            cap = int(st.status[0]) & 0xFFFFFFFF
         else:
-            check(L.gsb_preprocess(ctypes.byref(st.cam), ctypes.byref(g), st.geom.data_ptr(), geom_bytes,
-                                   radii.data_ptr(), None, stream), "gsb_preprocess")
             cap = int(est * HEADROOM) + 65536
         _render_phase(st, cap, dev)
         if est is None:

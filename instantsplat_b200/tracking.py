@@ -56,7 +56,7 @@ class PoseTracker:
         self.radii = torch.empty(self.P, dtype=torch.int32, device=self.dev)
         self.color = torch.empty(3, self.H, self.W, dtype=torch.float32, device=self.dev)
         self.dL = torch.empty_like(self.color)
-        self.host_status = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.host_status = torch.zeros(8, dtype=torch.int32).pin_memory()
         self.cap, self.binning, self.bin_bytes = 0, None, 0
         self.headroom = 1.6            # the pose moves during tracking, and with it the instance count
         self.R_seen = 0

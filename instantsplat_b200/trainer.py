@@ -80,7 +80,7 @@ def _align(n, a=64):
 class JointTrainer:
     def __init__(self, scene: Scene, device, gt_images: Optional[torch.Tensor] = None,
                  cfg: Optional[OptimConfig] = None, world_size: int = 1, rank: int = 0,
-                 process_group=None, exchange: str = "allreduce"):
+                 process_group=None, exchange: str = "allreduce", use_graph: bool = False):
         self.cfg = cfg or OptimConfig()
         self.dev = torch.device(device)
         self.world_size, self.rank, self.pg = world_size, rank, process_group
@@ -162,7 +162,7 @@ class JointTrainer:
         self.dL_dimg = torch.empty_like(self.color)
         self.maps = torch.empty(3, 3, self.H, self.W, dtype=torch.float32, device=self.dev)
         self.sums = torch.zeros(2, dtype=torch.float64, device=self.dev)
-        self.host_status = torch.zeros(2, 4, dtype=torch.int32).pin_memory()   # [0] after preprocess, [1] after render
+        self.host_status = torch.zeros(2, 8, dtype=torch.int32).pin_memory()   # [0] after preprocess, [1] after render
         self._ev_pre = torch.cuda.Event()
         self._status_dev = L.gsb_status_device(self.geom.data_ptr(), P)        # device address of the status words
         so = self._status_dev - self.geom.data_ptr()
@@ -172,6 +172,16 @@ class JointTrainer:
         self._pose_flags = torch.zeros(8, dtype=torch.int32, device=self.dev)
         if world_size > 1:    # the word the optimizer kernels test: overflow flags summed over the ranks
             self._ovf = self.flags[7:8] if self._fused else self._pg_buf[-1:]
+        # CUDA-graph replay of the whole iteration (single GPU): one graph per (view, ground-truth buffer); everything
+        # that changes from step to step reaches the kernels through device memory (Adam step sizes) or is part of
+        # the graph's identity (view pose row, active SH degree, binning capacity)
+        self.use_graph = bool(use_graph) and world_size == 1
+        self._graphs = {}
+        self._step_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._step_dev = torch.zeros(8, dtype=torch.float32, device=self.dev)
+        self._status_t.zero_()        # the forward serial number lives in these words
+        self._fwd_count = 0
+        self._polling = False
         self.iteration = 0            # reference iterations = views consumed (by all ranks)
         self.opt_step = 0
         self.last_R = 0
@@ -233,12 +243,16 @@ class JointTrainer:
         L = _lib.lib()
         st = _lib.stream_ptr()
         cam, g = self._cam(), self._gauss(view)
+        capturing = torch.cuda.is_current_stream_capturing()
         check(L.gsb_preprocess(ctypes.byref(cam), ctypes.byref(g), self.geom.data_ptr(), self.geom_bytes,
                                self.radii.data_ptr(), self.host_status[0].data_ptr(), st), "gsb_preprocess")
-        self._ev_pre.record()
-        if self.cap == 0:                                   # very first forward: size the buffer from the real count
-            self._ev_pre.synchronize()
-            self._size_binning(int(self.host_status[0, 0]) & 0xFFFFFFFF)
+        if not capturing:
+            self._fwd_count += 1
+            self._polling = False
+            self._ev_pre.record()
+            if self.cap == 0:                               # very first forward: size the buffer from the real count
+                self._ev_pre.synchronize()
+                self._size_binning(int(self.host_status[0, 0]) & 0xFFFFFFFF)
         check(L.gsb_render(ctypes.byref(cam), self.P, self.geom.data_ptr(), self.binning.data_ptr(),
                            self.bin_bytes, self.cap, self.image_buf.data_ptr(), self.color.data_ptr(),
                            self.host_status[1].data_ptr(), st), "gsb_render")
@@ -248,7 +262,18 @@ class JointTrainer:
         """Wait for the status words of the last forward's preprocess phase (early in the stream: the GPU still has
         the rest of the iteration queued, so this never starves it).  Returns True if the binning buffer was big
         enough; otherwise grows it (the device skipped the optimizer update by itself) and returns False."""
-        self._ev_pre.synchronize()
+        if self._polling:
+            # graph replay: no host-visible event inside the graph, so watch the pinned status words for this forward's
+            # serial number (written by the tile scan, copied by the memcpy node right behind it)
+            want = self._fwd_count & 0x7FFFFFFF
+            hs = self.host_status
+            n = 0
+            while (int(hs[0, 6]) & 0x7FFFFFFF) != want:
+                n += 1
+                if n > 20_000_000:
+                    raise _lib.GsbError("graph replay: the forward's status words never arrived")
+        else:
+            self._ev_pre.synchronize()
         R = int(self.host_status[0, 0]) & 0xFFFFFFFF
         self.last_R = R
         if R > self.cap:
@@ -301,11 +326,29 @@ class JointTrainer:
             self._pg_buf[-1:].copy_(self._status_t[1:2])
             allreduce_sum_((self.grads, self._pg_buf), self.pg)
 
-    def optimizer_step(self, grad_scale: Optional[float] = None) -> None:
+    def _step_sizes(self):
+        """lr * sqrt(1-b2^t)/(1-b1^t) per tensor for the current counters (host, double)."""
+        c = self.cfg
+        t = max(1, self.opt_step)
+        corr = (1 - 0.999 ** t) ** 0.5 / (1 - 0.9 ** t)
+        lrs = self._lrs()
+        out = [lrs[name] * corr for name, _ in SEGMENTS]
+        if c.optim_pose:
+            out.append(self.cam_sched(self.iteration) * corr)
+        return out
+
+    def _upload_step_sizes(self) -> None:
+        ss = self._step_sizes()
+        for i, v in enumerate(ss):
+            self._step_host[i] = v
+        self._step_dev.copy_(self._step_host, non_blocking=True)
+
+    def optimizer_step(self, grad_scale: Optional[float] = None, _advance: bool = True, _dev_steps: bool = False) -> None:
         """PerPointAdam.step over the 6 Gaussian tensors + the pose table in one launch
         (param groups and LRs of /root/reference/scene/gaussian_model.py:203-243)."""
         c = self.cfg
-        self.opt_step += 1
+        if _advance:
+            self.opt_step += 1
         t = self.opt_step
         b1, b2, eps = 0.9, 0.999, 1e-15
         corr = (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
@@ -323,7 +366,7 @@ class JointTrainer:
             entries.append(dict(param=self.poses, grad=self.pose_grad, exp_avg=self.pose_m, exp_avg_sq=self.pose_v,
                                 per_point_lr=None, row_len=7, step_size=self.cam_sched(self.iteration) * corr,
                                 beta1=b1, beta2=b2, eps=eps, weight_decay=0.0, grad_scale=gs))
-        launch_adam(entries, self.flags, skip_ptr=self._skip_ptr())
+        launch_adam(entries, self.flags, skip_ptr=self._skip_ptr(), step_sizes_dev=self._step_dev if _dev_steps else None)
 
     def _skip_ptr(self):
         """Device word that makes the optimizer kernels skip the update: the forward's overflow status
@@ -405,6 +448,33 @@ class JointTrainer:
         else:
             dist.all_reduce(self._sync, group=self.pg)
 
+    def _graph_iteration(self, view: int, gt: torch.Tensor, do_opt: bool) -> None:
+        """Replay (capturing on first use) the CUDA graph of one iteration on `view`."""
+        if do_opt:
+            self.opt_step += 1
+            self._upload_step_sizes()                    # stream-ordered before the replay
+        for _attempt in range(2):
+            key = (view, gt.data_ptr(), do_opt, self.active_sh_degree, self.cap, self.exact_cull)
+            g = self._graphs.get(key)
+            if g is None:
+                if len(self._graphs) > 64:
+                    self._graphs.clear()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_forward(view)
+                    self.loss_and_backward(view, gt)
+                    if do_opt:
+                        self.optimizer_step(_advance=False, _dev_steps=True)
+                self._graphs[key] = g
+            self._fwd_count += 1
+            self._polling = True
+            g.replay()
+            if self._settle():
+                return
+            # capacity exceeded: the device skipped the update, the buffer has been enlarged -> new graph, once more
+        raise _lib.GsbError("graph replay: binning capacity exceeded twice in a row")
+
     def _run_iteration(self, view: int, gt: torch.Tensor, do_opt: bool) -> None:
         self._launch_forward(view)
         self.loss_and_backward(view, gt)
@@ -448,6 +518,9 @@ class JointTrainer:
         if gt is None:
             gt = self.gt[view]
         do_opt = self.iteration < c.iterations
+        if self.use_graph and self.cap > 0:
+            self._graph_iteration(view, gt, do_opt)
+            return
         self._run_iteration(view, gt, do_opt)
         if not self._settle():
             # The binning capacity was exceeded: the device skipped the update by itself (gated on the overflow word,
@@ -497,6 +570,9 @@ class JointTrainer:
         self._status_t = self.geom[so:so + 32].view(torch.int32)
         self.cap = 0                                  # the next forward sizes the binning buffer from the new count
         self._keep = None
+        self._graphs.clear()
+        self._status_t.zero_()
+        self._fwd_count = 0
 
     def _set_per_point_lr(self, values: Optional[torch.Tensor]) -> None:
         if values is None:

@@ -200,6 +200,33 @@ def test_exact_cull_is_lossless():
         assert rel_err(a_g[k], b_g[k]) < 1e-4, k
 
 
+def test_sync_free_capacity_overflow_is_repaired():
+    """The autograd boundary sizes the binning buffer from earlier counts and checks lazily.  With a (forced) far too
+    small estimate the forward truncates its tile lists, the check at the backward notices, repeats the render phase in
+    place with an exact buffer (RuntimeWarning) and the results equal those of an exactly sized call."""
+    import instantsplat_b200.rasterizer as R
+    sc = random_scene(24000, 200, 136, seed=3)
+    bg = torch.tensor([0.0, 0.1, 0.0])
+    gt = torch.rand(3, sc.height, sc.width, generator=torch.Generator().manual_seed(2))
+    a_img, a_r, a_loss, a_g = cuda_run(sc, 3, bg, gt)
+    key = (torch.zeros(1, device=DEV).device.index, sc.P, sc.width, sc.height)
+    assert R._last_R.get(key, 0) > 65536, "scene too small to overflow the minimum capacity"
+    true_R, saved = None, R.HEADROOM
+    try:
+        R.HEADROOM = 0.0                     # capacity = 0 * estimate + 65536 instances
+        R._last_R[key] = 1
+        with pytest.warns(RuntimeWarning):
+            b_img, b_r, b_loss, b_g = cuda_run(sc, 3, bg, gt)
+        true_R = R._last_R[key]
+    finally:
+        R.HEADROOM = saved
+    assert true_R > 65536
+    assert torch.equal(a_r, b_r) and float((a_img - b_img).abs().max()) <= 1e-6
+    assert abs(float(a_loss) - float(b_loss)) < 1e-6
+    for k in NAMES + ("pose",):
+        assert rel_err(b_g[k], a_g[k]) < 1e-4, k
+
+
 def test_blend_kernel_versions_agree():
     """v1 (one pixel per lane) and v2 (two pixels, packed f32x2) blend kernels, with and without TMA bulk
     staging, on a scene whose image size is not a multiple of the tile size."""

@@ -200,3 +200,38 @@ def test_densify_prune_reset_state_surgery_vs_reference_golden(golden_dir):
     close(gm._opacity, z["reset_opacity"], "model reset_opacity")
     gm_step("s5")
     assert gm.get_xyz.shape[0] == tr.P
+
+
+def test_graph_replay_matches_eager_and_survives_overflow():
+    """JointTrainer(use_graph=True) replays each view's iteration from a CUDA graph (step sizes through device memory,
+    R never on the host).  Same losses as the eager trainer; and when the binning capacity is exceeded (forced here)
+    the device-gated optimizer skips the update, the host notices lazily, enlarges the buffer and repeats the iteration
+    -- in both launch modes -- ending where an undisturbed trainer ends."""
+    import instantsplat_b200 as I
+    sc, gts, cams = make_inputs(P=30_000, W=256, H=160, seed=53)
+    n = 12
+    views = [k % sc.n_views for k in range(n)]
+
+    def run(use_graph, sabotage_at=None):
+        tr = I.JointTrainer(sc, DEV, gt_images=gts, use_graph=use_graph)
+        losses = []
+        for k in range(n):
+            if k == sabotage_at:
+                tr._size_binning(0)                  # capacity 65536 instances: far below the real count
+                assert tr.cap < tr.last_R
+            tr.step(views[k])
+            losses.append(float(tr.loss_value()))
+        torch.cuda.synchronize()
+        return tr, losses
+
+    eager, l_eager = run(False)
+    graph, l_graph = run(True)
+    assert len(graph._graphs) >= sc.n_views, "every view should have been captured"
+    assert max(abs(a - b) for a, b in zip(l_eager, l_graph)) < 1e-5, (l_eager, l_graph)
+    assert graph.opt_step == eager.opt_step == n and graph.iteration == eager.iteration == n
+    for use_graph in (False, True):
+        tr, l_ovf = run(use_graph, sabotage_at=7)
+        assert tr.overflows == 1 and tr.opt_step == n
+        assert max(abs(a - b) for a, b in zip(l_eager, l_ovf)) < 1e-5, (use_graph, l_eager, l_ovf)
+        d = float((tr.params - eager.params).abs().max())
+        assert d < 5e-3, d                           # same trajectory up to atomic-order noise through Adam

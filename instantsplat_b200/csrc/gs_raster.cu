@@ -461,7 +461,7 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int pose_only_layout, OutPtrs out
           ds[2] *= -0.5f;
           ds[3] = -ds[3];
           ds[4] *= -0.5f;
-          ds[5] = ds[5] / p.opacity;
+          ds[5] = p.opacity > 0.f ? ds[5] / p.opacity : 0.f;     // contributing pairs have opacity >= 1/255
         }
         project_bwd(*cam, g, p, row_rest, use_sh, in.cov3D != nullptr, ds, gg, row_dc, row_rest, pa);
         has = use_sh;

@@ -244,17 +244,33 @@ def _backward(st: _State, dL_dout, want, dev):
     return out
 
 
+def _debug_snapshot(path: str, args) -> None:
+    """Upstream's wrapper, in debug mode, saves the arguments of a failing call (snapshot_fw.dump / snapshot_bw.dump)
+    before re-raising, so that the failure can be replayed."""
+    try:
+        torch.save(tuple(a.detach().cpu() if torch.is_tensor(a) else a for a in args), path)
+        print(f"\nAn error occured in {'forward' if 'fw' in path else 'backward'}. Writing {path} for debugging.")
+    except Exception as e:            # never mask the original error
+        print(f"(could not write {path}: {e})")
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                 raster_settings):
         has = lambda t: t is not None and t.numel() > 0
         M = sh.shape[1] if has(sh) else 1
-        color, radii, st = _forward(
-            raster_settings, means3D, scales if has(scales) else None,
-            rotations if has(rotations) else None, opacities.reshape(-1) if opacities.dim() > 1 else opacities,
-            sh if has(sh) else None, None, 1, M, colors_precomp if has(colors_precomp) else None,
-            cov3Ds_precomp if has(cov3Ds_precomp) else None, None, 0)
+        try:
+            color, radii, st = _forward(
+                raster_settings, means3D, scales if has(scales) else None,
+                rotations if has(rotations) else None, opacities.reshape(-1) if opacities.dim() > 1 else opacities,
+                sh if has(sh) else None, None, 1, M, colors_precomp if has(colors_precomp) else None,
+                cov3Ds_precomp if has(cov3Ds_precomp) else None, None, 0)
+        except Exception:
+            if raster_settings.debug:
+                _debug_snapshot("snapshot_fw.dump", (means3D, sh, colors_precomp, opacities, scales, rotations,
+                                                     cov3Ds_precomp, tuple(raster_settings)))
+            raise
         ctx.st = st
         # registered only so that autograd's version counters catch in-place edits between forward and backward
         # (the backward re-projects from the live input buffers)
@@ -268,10 +284,15 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out_color, _grad_radii):
         st = ctx.st
-        _ = ctx.saved_tensors
-        g = _backward(st, grad_out_color, None, grad_out_color.device)
-        if ctx.debug:
-            torch.cuda.synchronize()
+        saved = ctx.saved_tensors
+        try:
+            g = _backward(st, grad_out_color, None, grad_out_color.device)
+            if ctx.debug:
+                torch.cuda.synchronize()
+        except Exception:
+            if ctx.debug:
+                _debug_snapshot("snapshot_bw.dump", tuple(saved) + (grad_out_color,))
+            raise
         return (g["means3D"], g["means2D"], g.get("sh"), g.get("colors"),
                 g["opacities"].reshape(ctx.shapes[0]), g.get("scales"), g.get("rotations"), g.get("cov3D"),
                 None)

@@ -146,3 +146,18 @@ def test_bench_reference_arm_prints_one_json_line():
               "cpu_baseline", "e2e", "config"):
         assert k in d, k
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+
+
+def test_debug_mode_writes_snapshot_of_failing_call(tmp_path, monkeypatch):
+    """Upstream's Python wrapper dumps the arguments of a failing forward to snapshot_fw.dump in debug mode and
+    re-raises (boundary B2 error behaviour)."""
+    import instantsplat_b200 as I
+    monkeypatch.chdir(tmp_path)
+    eye = torch.eye(4)
+    rs = I.GaussianRasterizationSettings(32, 32, 1.0, 1.0, torch.zeros(3), 1.0, eye, eye, 0, torch.zeros(3), False, True)
+    bad = torch.zeros(5, 4)                       # means3D must be [P,3]
+    with pytest.raises(RuntimeError):
+        I.GaussianRasterizer(rs)(means3D=bad, means2D=torch.zeros(5, 3), opacities=torch.ones(5, 1),
+                                 colors_precomp=torch.ones(5, 3), scales=torch.ones(5, 3), rotations=torch.ones(5, 4))
+    dump = torch.load(tmp_path / "snapshot_fw.dump", weights_only=False)
+    assert tuple(dump[0].shape) == (5, 4) and dump[-1][0] == 32

@@ -42,7 +42,14 @@ __global__ void __launch_bounds__(kScanT) k_tile_scan(GeomView gv, int ntiles) {
   const int lo = tid * per, hi = min(ntiles, lo + per);
   unsigned long long sum = 0;
   uint32_t mx = 0;
-  for (int t = lo; t < hi; ++t) { const uint32_t c = gv.tcount[t]; sum += c; mx = max(mx, c); }
+  // eight independent loads in flight per trip (the kernel is one CTA on the critical path: latency is everything)
+  for (int t0 = lo; t0 < hi; t0 += 8) {
+    uint32_t c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) c[u] = t0 + u < hi ? gv.tcount[t0 + u] : 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { sum += c[u]; mx = max(mx, c[u]); }
+  }
   unsigned long long inc = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -67,13 +74,22 @@ __global__ void __launch_bounds__(kScanT) k_tile_scan(GeomView gv, int ntiles) {
   }
   __syncthreads();
   unsigned long long run = (inc - sum) + (warp ? s_warp[warp - 1] : 0ull);
-  for (int t = lo; t < hi; ++t) {
-    const uint32_t c = gv.tcount[t];
-    gv.tstart[t] = (uint32_t)min(run, 0xFFFFFFF0ull);     // saturating: such a tile is beyond any capacity
-    gv.tcursor[t] = 0u;
-    run += c;
-    if (c > kLargeList) gv.q_huge[atomicAdd(&s_nq[1], 1u)] = (uint32_t)t;        // rare: long lists are queued for
-    else if (c > kSmallList) gv.q_large[atomicAdd(&s_nq[0], 1u)] = (uint32_t)t;  // the persistent sort kernels
+  for (int t0 = lo; t0 < hi; t0 += 8) {
+    uint32_t cc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cc[u] = t0 + u < hi ? gv.tcount[t0 + u] : 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int t = t0 + u;
+      if (t < hi) {
+        const uint32_t c = cc[u];
+        gv.tstart[t] = (uint32_t)min(run, 0xFFFFFFF0ull);     // saturating: such a tile is beyond any capacity
+        gv.tcursor[t] = 0u;
+        run += c;
+        if (c > kLargeList) gv.q_huge[atomicAdd(&s_nq[1], 1u)] = (uint32_t)t;        // rare: long lists are queued for
+        else if (c > kSmallList) gv.q_large[atomicAdd(&s_nq[0], 1u)] = (uint32_t)t;  // the persistent sort kernels
+      }
+    }
   }
   __syncthreads();
   if (tid == kScanT - 1) {

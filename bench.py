@@ -494,6 +494,7 @@ def run_b200(args):
             del model
         finally:
             RD.FUSED = True
+    tr.check_peer_errors()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -84,7 +84,6 @@ __global__ void __launch_bounds__(kScanT) k_tile_scan(GeomView gv, int ntiles) {
       if (t < hi) {
         const uint32_t c = cc[u];
         gv.tstart[t] = (uint32_t)min(run, 0xFFFFFFF0ull);     // saturating: such a tile is beyond any capacity
-        gv.tcursor[t] = 0u;
         run += c;
         if (c > kLargeList) gv.q_huge[atomicAdd(&s_nq[1], 1u)] = (uint32_t)t;        // rare: long lists are queued for
         else if (c > kSmallList) gv.q_large[atomicAdd(&s_nq[0], 1u)] = (uint32_t)t;  // the persistent sort kernels
@@ -363,6 +362,9 @@ int gsb_launch_binning(int P, const GeomView& gv, const BinView& bv, int W, int 
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int gx = (W + kBlock - 1) / kBlock, gy = (H + kBlock - 1) / kBlock;
+  // the emission cursors are reset HERE (not by the scan) so that the render phase can be repeated on the same
+  // preprocess result, e.g. with a larger buffer after an overflow
+  GSB_CUDA(cudaMemsetAsync(gv.tcursor, 0, (size_t)gx * gy * 4, st));
   if (P > 0) {
     ProfScope ps(GSB_K_DUPLICATE, st);
     k_scatter<<<(P + kThreads - 1) / kThreads, kThreads, 0, st>>>(P, gv, bv, W, H, gx, exact_cull, cap);

@@ -152,7 +152,7 @@ static inline ImgView img_view(void* base, int W, int H) {
 }  // namespace gsb
 
 // ---- launchers implemented in gs_bin.cu / gs_blend.cu -----------------------------------------
-// tile scan: tstart = exclusive scan(tcount), tcursor = 0, status = {R, 0, max list, 0}
+// tile scan: tstart = exclusive scan(tcount), status = {R, 0, max list, 0, long-list queue lengths, serial}
 int gsb_launch_tile_scan(const gsb::GeomView& gv, int ntiles, cudaStream_t st);
 // scatter + per-tile (depth, id) sort + slab gather + ranges; cap = instance capacity of the binning buffer
 int gsb_launch_binning(int P, const gsb::GeomView& gv, const gsb::BinView& bv, int W, int H, int exact_cull,

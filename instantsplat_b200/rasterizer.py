@@ -38,12 +38,18 @@ class GaussianRasterizationSettings(NamedTuple):
 
 EXACT_CULL = True   # lossless alpha<1/255 tile culling (set False for the reference's rect-only binning)
 
-# The instance count R (number of (Gaussian, tile) pairs) never has to reach the host: the kernels read it from
-# device memory.  The host only chooses the CAPACITY of the binning buffer.  SYNC_FREE = True sizes it from the
-# last count seen for the same (device, P, W, H) with 50 % headroom and verifies lazily (at the backward, or at
-# the next forward) that it was enough; the very first call of a shape -- and every call when SYNC_FREE is False
-# -- waits for R once and sizes the buffer exactly, like the reference's blocking cudaMemcpy of num_rendered.
+# The instance count R (number of (Gaussian, tile) pairs) never has to reach the host BEFORE the render phase is
+# launched: the kernels read it from device memory, the host only chooses the CAPACITY of the binning buffer.
+# SYNC_FREE = True sizes it from the counts seen for the same (device, P, W, H) with 50 % headroom, enqueues binning
+# and blend, and only then waits for the status words of the PREPROCESS phase (an event right behind the tile scan):
+# while the host waits, the GPU has the whole render phase queued, so it never idles -- unlike the reference's
+# blocking cudaMemcpy of num_rendered, which stalls the GPU until the host has sized its buffers and launched the
+# rest.  If the capacity was exceeded (rare), the render phase is repeated with an exact buffer before the forward
+# returns, so whatever the caller computes from the image is consistent.  LAZY_VERIFY = True postpones the check to
+# the backward / the next forward instead (forward-only loops that never look at R); the very first call of a shape
+# -- and every call when SYNC_FREE is False -- waits for R before launching the render phase and sizes it exactly.
 SYNC_FREE = True
+LAZY_VERIFY = False
 HEADROOM = 1.5
 _last_R = {}            # (device index, P, W, H) -> last verified instance count
 _pending = {}           # same key -> _State whose capacity check has not been read yet
@@ -192,8 +198,10 @@ def _forward(settings, means3D, scales, rotations, opacities, sh_dc, sh_rest, sh
         if est is None:
             _note_R(st.key, cap)
             st.checked, st.R_true = True, cap
-        else:
+        elif LAZY_VERIFY:
             _pending[st.key] = (weakref.ref(st), st.status, st.event, cap)
+        else:
+            _verify(st, dev)             # waits for the preprocess phase only; repeats the render phase on overflow
         if settings.debug:
             torch.cuda.synchronize()
     return st.color, radii, st

@@ -201,9 +201,10 @@ def test_exact_cull_is_lossless():
 
 
 def test_sync_free_capacity_overflow_is_repaired():
-    """The autograd boundary sizes the binning buffer from earlier counts and checks lazily.  With a (forced) far too
-    small estimate the forward truncates its tile lists, the check at the backward notices, repeats the render phase in
-    place with an exact buffer (RuntimeWarning) and the results equal those of an exactly sized call."""
+    """The autograd boundary sizes the binning buffer from earlier counts and launches the render phase without waiting
+    for the instance count.  With a (forced) far too small estimate the tile lists are truncated; the check at the end of
+    the forward notices, repeats the render phase with an exact buffer (RuntimeWarning) and image, loss and gradients
+    equal those of an exactly sized call."""
     import instantsplat_b200.rasterizer as R
     sc = random_scene(24000, 200, 136, seed=3)
     bg = torch.tensor([0.0, 0.1, 0.0])

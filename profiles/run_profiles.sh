@@ -9,11 +9,10 @@ OUT=gpurun_out
 mkdir -p $OUT
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/${TAG}_launches.csv \
     python profiles/prof_step.py --steps 3 > $OUT/${TAG}_launches.log 2>&1
-KERNELS=${2:-"k_blend_bwd2 k_blend_fwd2 k_preprocess_bwd k_preprocess\\( k_tile_sort k_scatter k_ssim_fwd k_ssim_bwd k_adam\\("}
+KERNELS=${2:-"k_blend_bwd2 k_blend_fwd2 k_preprocess_bwd k_preprocess\$ k_tile_sort\$ k_scatter k_ssim_fwd k_ssim_bwd k_adam\$"}
 for k in $KERNELS; do
-  name=$(echo $k | tr -d '\\(')
+  name=$(echo $k | tr -d '\\($')
   SKIP=2
-  if [ "$name" = "k_tile_sort" ]; then SKIP=3; fi    # three size classes per step: capture the small-list class of step 2
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s $SKIP -c 1 -f -o $OUT/${TAG}_$name \
       python profiles/prof_step.py --steps 3 > $OUT/${TAG}_$name.log 2>&1
 done

@@ -12,8 +12,9 @@
 //                  through per-tile atomic cursors
 //   k_tile_sort    one CTA per tile: the segment is sorted by the unique 64-bit key in SHARED MEMORY
 //                  (one adaptive-range bucket pass + per-bucket insertion sort; flip-bitonic fallback for
-//                  skewed depth distributions), then the splat records are gathered into the tile's contiguous
-//                  slab (3 x float4 per instance) that the blend kernels stage with TMA bulk copies
+//                  skewed depth distributions) and written out as the tile's id list.  No per-instance copy of the
+//                  splat records is materialised: the blend kernels stage id chunks with TMA bulk copies and gather
+//                  the 48-byte records with cp.async out of the L2-resident record table, only as far as they walk
 //
 // Result order = (tile, depth bits ascending, Gaussian index ascending): exactly the reference's stable radix
 // sort of keys emitted in index order (Appendix A.2.9) -- deterministic although emission uses atomics.
@@ -121,16 +122,16 @@ k_scatter(int P, GeomView gv, BinView bv, int W, int H, int gx, int exact_cull, 
   TileSink sink{gv.tcount, gv.tstart, gv.tcursor, bv.pairs, cap};
   uint32_t mask = 0u;
   if (n) {
-    const uint2 rc = gv.rect[i];
-    p.rx0 = rc.x & 0xFFFF; p.rx1 = rc.x >> 16; p.ry0 = rc.y & 0xFFFF; p.ry1 = rc.y >> 16;
-    const float4 b = gv.Codq[i];
-    key = ((unsigned long long)__float_as_uint(b.z) << 32) | (unsigned long long)(uint32_t)i;
+    const float4 r3 = gv.rec[4 * (size_t)i + 3];             // depth, rect x, rect y, keep mask
+    const uint32_t rcx = __float_as_uint(r3.y), rcy = __float_as_uint(r3.z);
+    p.rx0 = rcx & 0xFFFF; p.rx1 = rcx >> 16; p.ry0 = rcy & 0xFFFF; p.ry1 = rcy >> 16;
+    key = ((unsigned long long)__float_as_uint(r3.x) << 32) | (unsigned long long)(uint32_t)i;
     coop = (p.rx1 - p.rx0) * (p.ry1 - p.ry0) > kCoopTiles;
-    if (coop) {
-      const float4 a = gv.xyAB[i];
-      p.x = a.x; p.y = a.y; p.A = a.z; p.B = a.w; p.C = b.x; p.qthr = b.w;
+    if (coop) {                                              // re-walk the rect from the stored record (log2 domain)
+      const float4 e0 = gv.rec[4 * (size_t)i], e1 = gv.rec[4 * (size_t)i + 1];
+      p.x = e0.x; p.y = e0.y; p.A = -e0.z; p.B = -0.5f * e0.w; p.C = -e1.x; p.qthr = e1.z;
     } else {
-      mask = gv.kmask[i];        // exactly the tiles k_preprocess counted
+      mask = __float_as_uint(r3.w);                          // exactly the tiles k_preprocess counted
     }
   }
   warp_sink_masks(mask, p.rx0, p.ry0, p.rx1 - p.rx0, gx, sink, key);
@@ -170,37 +171,16 @@ __device__ __forceinline__ void cta_bitonic(unsigned long long* a, uint32_t n) {
   }
 }
 
-// Gather the splat records of a sorted id list into the tile's slab.  kGU entries per thread per round with all
-// their 16-byte loads issued before the first store (the loads are scattered L2 hits: latency, not bandwidth).
-constexpr int kGU = 2;
-__device__ __forceinline__ void gather_slab(const GeomView& gv, const BinView& bv, const unsigned long long* sorted,
-                                            uint32_t start, uint32_t n, int nthreads) {
-  for (uint32_t j0 = threadIdx.x; j0 < n; j0 += kGU * nthreads) {
-    uint32_t id[kGU];
-    float4 a[kGU], b[kGU], c[kGU];
-#pragma unroll
-    for (int u = 0; u < kGU; ++u) {
-      const uint32_t j = j0 + u * nthreads;
-      id[u] = j < n ? (uint32_t)sorted[j] : 0xFFFFFFFFu;
-    }
-#pragma unroll
-    for (int u = 0; u < kGU; ++u)
-      if (id[u] != 0xFFFFFFFFu) { a[u] = gv.xyAB[id[u]]; b[u] = gv.Codq[id[u]]; c[u] = gv.rgbr[id[u]]; }
-#pragma unroll
-    for (int u = 0; u < kGU; ++u)
-      if (id[u] != 0xFFFFFFFFu) {
-        const size_t e = (size_t)start + j0 + u * nthreads;
-        // conic pre-scaled into the log2 domain: power*log2(e) = A' dx^2 + B' dx dy + C' dy^2
-        bv.s0[e] = make_float4(a[u].x, a[u].y, -0.5f * kLog2e * a[u].z, -kLog2e * a[u].w);
-        bv.s1[e] = make_float4(-0.5f * kLog2e * b[u].x, b[u].y, 0.5f * kLog2e * b[u].w, __uint_as_float(id[u]));
-        bv.s2[e] = make_float4(c[u].x, c[u].y, c[u].z, 0.f);
-      }
-  }
+// Write the tile's sorted id list (the blend kernels gather the splat records themselves, and only for the part of
+// the list they actually walk: early termination stops most tiles after a fraction of their entries).
+__device__ __forceinline__ void write_ids(const BinView& bv, const unsigned long long* sorted, uint32_t start, uint32_t n,
+                                          int nthreads) {
+  for (uint32_t j = threadIdx.x; j < n; j += nthreads) bv.ids[(size_t)start + j] = (uint32_t)sorted[j];
 }
 
 constexpr uint32_t kSkew = 24;     // a bucket longer than this sends the tile to the bitonic fallback
 
-// Sorts one tile's segment and gathers its slab.  NT threads, KPT keys per thread (lists of up to NT*KPT entries);
+// Sorts one tile's segment and writes its id list.  NT threads, KPT keys per thread (lists of up to NT*KPT entries);
 // HUGE: any length, sorted in global memory.
 //
 // Shared-memory sort: one bucket pass over the tile's own depth range -- bucket(d) = floor((d - dmin) * CAP /
@@ -232,7 +212,7 @@ __device__ __forceinline__ void tile_sort_one(const GeomView& gv, const BinView&
   const unsigned long long* seg = bv.pairs + start;
   if (HUGE) {
     cta_bitonic<NT>(const_cast<unsigned long long*>(seg), n);
-    gather_slab(gv, bv, seg, start, n, NT);
+    write_ids(bv, seg, start, n, NT);
     return;
   }
   __syncthreads();
@@ -313,7 +293,7 @@ __device__ __forceinline__ void tile_sort_one(const GeomView& gv, const BinView&
     }
     __syncthreads();
   }
-  gather_slab(gv, bv, sorted, start, n, NT);
+  write_ids(bv, sorted, start, n, NT);
 }
 
 // ---- kernels ------------------------------------------------------------------------------------------------

@@ -2,9 +2,14 @@
 // reference call site /root/reference/gaussian_renderer/__init__.py:126-135).
 //
 //   k_blend_fwd2 / k_blend_bwd2   CTA = 16x16 tile (4 warps), warp = 8x8 block, TWO pixels per lane sharing dx;
-//                                 per-pair math issued as packed f32x2 (FFMA2/FMUL2/FADD2); slab chunks staged by
-//                                 TMA bulk copies (cp.async.bulk + mbarrier), double buffered; per-warp
-//                                 ballot-compacted exact sub-tile culling
+//                                 per-pair math issued as packed f32x2 (FFMA2/FMUL2/FADD2); per-warp
+//                                 ballot-compacted exact sub-tile culling.  Staging, three-deep software pipeline:
+//                                 the tile's sorted ID chunk arrives by a TMA bulk copy (cp.async.bulk + mbarrier)
+//                                 two chunks ahead, the 48-byte splat records of those ids are GATHERED with
+//                                 cp.async (LDGSTS) out of the L2-resident record table one chunk ahead, the
+//                                 current chunk is blended from shared memory.  No per-instance copy of the records
+//                                 is ever written to HBM, and nothing is fetched for the part of a list that early
+//                                 termination never reaches.
 //   k_blend_fwd / k_blend_bwd     v1: one pixel per lane, 8 warps per tile, cooperative staging -- the first
 //                                 correct version, kept as the in-library cross-check (gsb_set_option)
 #include "gs_internal.cuh"
@@ -16,7 +21,7 @@ namespace {
 constexpr float kLn2 = 0.6931471805599453f;
 
 #ifndef GSB_CHUNK
-#define GSB_CHUNK 256
+#define GSB_CHUNK 224
 #endif
 #ifndef GSB_FWD_MINB
 #define GSB_FWD_MINB 7
@@ -60,8 +65,8 @@ __device__ __forceinline__ bool slab_may_contribute(const float4& e0, const floa
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_blend_fwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
-            const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+k_blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ ids, const float4* __restrict__ rec,
+            const float* __restrict__ bg, int W, int H, int gx,
             float* __restrict__ out_color, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
   __shared__ float4 sm0[kChunk1], sm1[kChunk1], sm2[kChunk1];
   const int tile = blockIdx.x;
@@ -82,10 +87,10 @@ k_blend_fwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, con
   for (int base = 0; base < n; base += kChunk1) {
     const int cnt = min(kChunk1, n - base);
     if ((int)threadIdx.x < cnt) {
-      size_t e = (size_t)rg.x + base + threadIdx.x;
-      sm0[threadIdx.x] = s0[e];
-      sm1[threadIdx.x] = s1[e];
-      sm2[threadIdx.x] = s2[e];
+      const float4* r = rec + 4 * (size_t)ids[(size_t)rg.x + base + threadIdx.x];
+      sm0[threadIdx.x] = r[0];
+      sm1[threadIdx.x] = r[1];
+      sm2[threadIdx.x] = r[2];
     }
     __syncthreads();
     if (!wdone) {
@@ -207,8 +212,8 @@ __device__ __forceinline__ void warp_reduce8(float* v, int lane) {
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_blend_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
-            const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+k_blend_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ ids, const float4* __restrict__ rec,
+            const float* __restrict__ bg, int W, int H, int gx,
             const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
             const float* __restrict__ dL_dpix, float* __restrict__ dacc) {
   __shared__ float4 sm0[kChunk1], sm1[kChunk1], sm2[kChunk1];
@@ -244,10 +249,10 @@ k_blend_bwd(const uint2* __restrict__ ranges, const float4* __restrict__ s0, con
     const int base = ch * kChunk1;
     const int cnt = min(kChunk1, bmax - base);
     if ((int)threadIdx.x < cnt) {
-      size_t e = (size_t)rg.x + base + threadIdx.x;
-      sm0[threadIdx.x] = s0[e];
-      sm1[threadIdx.x] = s1[e];
-      sm2[threadIdx.x] = s2[e];
+      const float4* r = rec + 4 * (size_t)ids[(size_t)rg.x + base + threadIdx.x];
+      sm0[threadIdx.x] = r[0];
+      sm1[threadIdx.x] = r[1];
+      sm2[threadIdx.x] = r[2];
     }
     __syncthreads();
     if (base < wmax) {
@@ -353,33 +358,80 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 struct SlabStage {
-  float4 s0[kChunk], s1[kChunk], s2[kChunk];
+  float4 s0[kChunk], s1[kChunk], s2[kChunk];     // record rows 0..2 of the chunk's entries: x,y,A',B' | C',o,qthr',id | r,g,b,-
 };
+constexpr int kIdRow = kChunk + 4;               // id chunk + up to 3 leading entries (bulk copies start 16-byte aligned)
 
-// Stage `cnt` slab entries starting at global entry `e0` into `dst`.  BULK: thread 0 issues three bulk copies
-// that complete on `bar`; otherwise all threads copy cooperatively (caller synchronises).
-template <bool BULK>
-__device__ __forceinline__ void stage_slab(SlabStage* dst, const float4* __restrict__ s0, const float4* __restrict__ s1,
-                                           const float4* __restrict__ s2, size_t e0, int cnt, uint64_t* bar,
-                                           int nthreads) {
-  if (BULK) {
-    if (threadIdx.x == 0) {
-      const uint32_t bytes = (uint32_t)cnt * 16u;
-      mbar_expect_tx(bar, 3u * bytes);
-      bulk_g2s(dst->s0, s0 + e0, bytes, bar);
-      bulk_g2s(dst->s1, s1 + e0, bytes, bar);
-      bulk_g2s(dst->s2, s2 + e0, bytes, bar);
-    }
-  } else {
-    for (int k = threadIdx.x; k < cnt; k += nthreads) {
-      dst->s0[k] = s0[e0 + k];
-      dst->s1[k] = s1[e0 + k];
-      dst->s2[k] = s2[e0 + k];
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The staging pipeline of one CTA over a sequence of chunks q = 0, 1, ... (chunk q = entries [e_q, e_q + cnt_q) of the
+// tile's sorted id list; the forward walks the list front to back, the backward back to front).
+//   request(q)  thread 0: TMA bulk copy of the id chunk into sid[q % 3], completing on bars[q % 3]
+//   gather(q)   all threads: wait for the ids, then cp.async the three record rows of every entry into stg[q & 1]
+//   land(more)  wait until the oldest outstanding gather has landed (more: a younger one is in flight) + CTA barrier
+// Schedule used by the kernels: request(0), request(1), gather(0); then per chunk q: gather(q+1), request(q+2), land,
+// blend chunk q, CTA barrier.  Every buffer is rewritten only after the barrier that ends its last reader.
+template <bool BULK, int NT>
+struct Stager {
+  SlabStage* stg;                 // [2]
+  uint32_t (*sid)[kIdRow];        // [3]   (BULK only)
+  uint64_t* bars;                 // [3]   (BULK only)
+  const uint32_t* ids;
+  const float4* rec;
+  int requested, waited;          // id chunks requested / consumed so far
+
+  __device__ __forceinline__ void init() {
+    requested = waited = 0;
+    if (BULK) {
+      if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
+      __syncthreads();
     }
   }
-}
-
-
+  __device__ __forceinline__ void request(int q, size_t e, int cnt) {
+    if (BULK) {
+      if (threadIdx.x == 0) {
+        const size_t ea = e & ~(size_t)3;
+        const uint32_t bytes = (uint32_t)(((e - ea) + (size_t)cnt + 3) & ~(size_t)3) * 4u;
+        mbar_expect_tx(&bars[q % 3], bytes);
+        bulk_g2s(sid[q % 3], ids + ea, bytes, &bars[q % 3]);
+      }
+      requested = q + 1;
+    }
+  }
+  __device__ __forceinline__ void gather(int q, size_t e, int cnt) {
+    SlabStage* st = &stg[q & 1];
+    if (BULK) {
+      mbar_wait(&bars[q % 3], (uint32_t)((q / 3) & 1));
+      waited = q + 1;
+      const uint32_t* row = sid[q % 3] + (e & 3);
+      for (int k = threadIdx.x; k < cnt; k += NT) {
+        const float4* r = rec + 4 * (size_t)row[k];
+        cp_async16(&st->s0[k], r); cp_async16(&st->s1[k], r + 1); cp_async16(&st->s2[k], r + 2);
+      }
+    } else {
+      for (int k = threadIdx.x; k < cnt; k += NT) {
+        const float4* r = rec + 4 * (size_t)__ldg(ids + e + k);
+        cp_async16(&st->s0[k], r); cp_async16(&st->s1[k], r + 1); cp_async16(&st->s2[k], r + 2);
+      }
+    }
+    cp_async_commit();
+  }
+  __device__ __forceinline__ void land(bool more) {
+    if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+  }
+  // never leave the kernel with copies in flight
+  __device__ __forceinline__ void drain() {
+    cp_async_wait<0>();
+    if (BULK)
+      for (int q = waited; q < requested; ++q) mbar_wait(&bars[q % 3], (uint32_t)((q / 3) & 1));
+  }
+};
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
@@ -388,17 +440,16 @@ __device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
 // (pixel, Gaussian) pairs each) and contributing pairs into stats[0..1].
 template <bool BULK, bool STATS = false>
 __global__ void __launch_bounds__(kThreads2, GSB_FWD_MINB)
-k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
-             const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+k_blend_fwd2(const uint2* __restrict__ ranges, const uint32_t* __restrict__ ids, const float4* __restrict__ rec,
+             const float* __restrict__ bg, int W, int H, int gx,
              float* __restrict__ out_color, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
              unsigned long long* __restrict__ stats = nullptr) {
   unsigned int st_iter = 0, st_valid = 0;
-  __shared__ __align__(128) SlabStage stg[BULK ? 2 : 1];
-  __shared__ __align__(8) uint64_t bars[2];
-  if (BULK) {
-    if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
-    __syncthreads();
-  }
+  __shared__ __align__(128) SlabStage stg[2];
+  __shared__ __align__(16) uint32_t sid[BULK ? 3 : 1][kIdRow];
+  __shared__ __align__(8) uint64_t bars[3];
+  Stager<BULK, kThreads2> sg{stg, sid, bars, ids, rec, 0, 0};
+  sg.init();
   const int tile = blockIdx.x;
   const int tx = tile % gx, ty = tile / gx;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -417,24 +468,23 @@ k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
   bool doneA = !inA, doneB = !inB;
   bool wdoneA = !(sx0 < W && sy0 < H), wdoneB = !(sx0 < W && sy0 + 4 < H);
   const int nch = (n + kChunk - 1) / kChunk;
-  if (BULK && nch > 0) stage_slab<true>(&stg[0], s0, s1, s2, (size_t)rg.x, min(kChunk, n), &bars[0], kThreads2);
-  int pending = -1;    // chunk whose bulk copy is in flight but has not been waited for
+  // chunk q = entries [rg.x + q*kChunk, ...) of the tile's list
+  auto c_e = [&](int q) { return (size_t)rg.x + (size_t)q * kChunk; };
+  auto c_n = [&](int q) { return min(kChunk, n - q * kChunk); };
+  if (nch > 0) {
+    sg.request(0, c_e(0), c_n(0));
+    if (nch > 1) sg.request(1, c_e(1), c_n(1));
+    sg.gather(0, c_e(0), c_n(0));
+  }
   for (int ci = 0; ci < nch; ++ci) {
     const int base = ci * kChunk;
     const int cnt = min(kChunk, n - base);
-    const SlabStage* cur = &stg[BULK ? (ci & 1) : 0];
-    if (BULK) {
-      pending = -1;
-      if (ci + 1 < nch) {     // prefetch the next chunk into the other stage (freed by the barrier below)
-        stage_slab<true>(&stg[(ci + 1) & 1], s0, s1, s2, (size_t)rg.x + base + kChunk, min(kChunk, n - base - kChunk),
-                         &bars[(ci + 1) & 1], kThreads2);
-        pending = ci + 1;
-      }
-      mbar_wait(&bars[ci & 1], (uint32_t)((ci >> 1) & 1));
-    } else {
-      stage_slab<false>(&stg[0], s0, s1, s2, (size_t)rg.x + base, cnt, nullptr, kThreads2);
-      __syncthreads();
+    const SlabStage* cur = &stg[ci & 1];
+    if (ci + 1 < nch) {          // keep the pipeline full: records of chunk ci+1, ids of chunk ci+2
+      sg.gather(ci + 1, c_e(ci + 1), c_n(ci + 1));
+      if (ci + 2 < nch) sg.request(ci + 2, c_e(ci + 2), c_n(ci + 2));
     }
+    sg.land(ci + 1 < nch);
     const float4* sm0 = cur->s0;
     const float4* sm1 = cur->s1;
     const float4* sm2 = cur->s2;
@@ -482,9 +532,8 @@ k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
       }
     }
     if (__syncthreads_and(wdoneA && wdoneB)) break;
-    pending = -1;
   }
-  if (BULK && pending >= 0) mbar_wait(&bars[pending & 1], (uint32_t)((pending >> 1) & 1));   // never exit with a copy in flight
+  sg.drain();
   if (STATS) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) st_valid += __shfl_xor_sync(0xffffffffu, st_valid, o);
@@ -509,16 +558,18 @@ k_blend_fwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
 // told about the layout (dacc[5] = dL/db, dacc[8] unused).
 template <bool BULK, bool STATS = false, bool POSE_ONLY = false>
 __global__ void __launch_bounds__(kThreads2, GSB_BWD_MINB)
-k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, const float4* __restrict__ s1,
-             const float4* __restrict__ s2, const float* __restrict__ bg, int W, int H, int gx,
+k_blend_bwd2(const uint2* __restrict__ ranges, const uint32_t* __restrict__ ids, const float4* __restrict__ rec,
+             const float* __restrict__ bg, int W, int H, int gx,
              const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
              const float* __restrict__ dL_dpix, float* __restrict__ dacc,
              unsigned long long* __restrict__ stats = nullptr) {
   unsigned int st_iter = 0, st_red = 0, st_valid = 0;
-  __shared__ __align__(128) SlabStage stg[BULK ? 2 : 1];
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(128) SlabStage stg[2];
+  __shared__ __align__(16) uint32_t sid[BULK ? 3 : 1][kIdRow];
+  __shared__ __align__(8) uint64_t bars[3];
   __shared__ int s_bmax;
-  if (BULK && threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  Stager<BULK, kThreads2> sg{stg, sid, bars, ids, rec, 0, 0};
+  sg.init();
   const int tile = blockIdx.x;
   const int tx = tile % gx, ty = tile / gx;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -555,24 +606,24 @@ k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
   float2 T = T_final;
   float2 acc_r = f2(0.f, 0.f), acc_g = f2(0.f, 0.f), acc_b = f2(0.f, 0.f);
   const int nchunks = (bmax + kChunk - 1) / kChunk;
-  // chunks are visited back to front; it = 0 is the LAST chunk
-  if (BULK && nchunks > 0)
-    stage_slab<true>(&stg[0], s0, s1, s2, (size_t)rg.x + (size_t)(nchunks - 1) * kChunk,
-                     min(kChunk, bmax - (nchunks - 1) * kChunk), &bars[0], kThreads2);
+  // chunks are visited back to front; pipeline step q = 0 is the LAST chunk
+  auto c_e = [&](int q) { return (size_t)rg.x + (size_t)(nchunks - 1 - q) * kChunk; };
+  auto c_n = [&](int q) { return min(kChunk, bmax - (nchunks - 1 - q) * kChunk); };
+  if (nchunks > 0) {
+    sg.request(0, c_e(0), c_n(0));
+    if (nchunks > 1) sg.request(1, c_e(1), c_n(1));
+    sg.gather(0, c_e(0), c_n(0));
+  }
   for (int it = 0; it < nchunks; ++it) {
     const int ch = nchunks - 1 - it;
     const int base = ch * kChunk;
     const int cnt = min(kChunk, bmax - base);
-    const SlabStage* cur = &stg[BULK ? (it & 1) : 0];
-    if (BULK) {
-      if (it + 1 < nchunks)
-        stage_slab<true>(&stg[(it + 1) & 1], s0, s1, s2, (size_t)rg.x + base - kChunk, kChunk, &bars[(it + 1) & 1],
-                         kThreads2);
-      mbar_wait(&bars[it & 1], (uint32_t)((it >> 1) & 1));
-    } else {
-      stage_slab<false>(&stg[0], s0, s1, s2, (size_t)rg.x + base, cnt, nullptr, kThreads2);
-      __syncthreads();
+    const SlabStage* cur = &stg[it & 1];
+    if (it + 1 < nchunks) {
+      sg.gather(it + 1, c_e(it + 1), c_n(it + 1));
+      if (it + 2 < nchunks) sg.request(it + 2, c_e(it + 2), c_n(it + 2));
     }
+    sg.land(it + 1 < nchunks);
     const float4* sm0 = cur->s0;
     const float4* sm1 = cur->s1;
     const float4* sm2 = cur->s2;
@@ -651,6 +702,7 @@ k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
     }
     __syncthreads();
   }
+  sg.drain();
   if (STATS) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) st_valid += __shfl_xor_sync(0xffffffffu, st_valid, o);
@@ -665,40 +717,40 @@ k_blend_bwd2(const uint2* __restrict__ ranges, const float4* __restrict__ s0, co
 
 }  // namespace
 
-int gsb_launch_blend_fwd(const BinView& bv, const ImgView& iv, const float* bg, int W, int H, float* out_color,
+int gsb_launch_blend_fwd(const GeomView& gv, const BinView& bv, const ImgView& iv, const float* bg, int W, int H, float* out_color,
                          cudaStream_t st) {
   const int gx = (W + kBlock - 1) / kBlock, gy = (H + kBlock - 1) / kBlock;
   ProfScope ps(GSB_K_BLEND_FWD, st);
   const int ver = gsb_option_blend_version(), bulk = gsb_option_stage_bulk();
   if (ver == 2 && bulk)
-    k_blend_fwd2<true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, out_color,
+    k_blend_fwd2<true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.ids, gv.rec, bg, W, H, gx, out_color,
                                                       iv.final_T, iv.n_contrib);
   else if (ver == 2)
-    k_blend_fwd2<false><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, out_color,
+    k_blend_fwd2<false><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.ids, gv.rec, bg, W, H, gx, out_color,
                                                        iv.final_T, iv.n_contrib);
   else
-    k_blend_fwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, out_color, iv.final_T,
+    k_blend_fwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.ids, gv.rec, bg, W, H, gx, out_color, iv.final_T,
                                               iv.n_contrib);
   GSB_CUDA(cudaGetLastError());
   return GSB_OK;
 }
 
-int gsb_launch_blend_bwd(const BinView& bv, const ImgView& iv, const float* bg, int W, int H, const float* dL_dout,
+int gsb_launch_blend_bwd(const GeomView& gv, const BinView& bv, const ImgView& iv, const float* bg, int W, int H, const float* dL_dout,
                          float* dacc, bool pose_only, cudaStream_t st) {
   const int gx = (W + kBlock - 1) / kBlock, gy = (H + kBlock - 1) / kBlock;
   ProfScope ps(GSB_K_BLEND_BWD, st);
   const int ver = gsb_option_blend_version(), bulk = gsb_option_stage_bulk();
   if (pose_only)
-    k_blend_bwd2<true, false, true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, iv.final_T,
+    k_blend_bwd2<true, false, true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.ids, gv.rec, bg, W, H, gx, iv.final_T,
                                                                    iv.n_contrib, dL_dout, dacc);
   else if (ver == 2 && bulk)
-    k_blend_bwd2<true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, iv.final_T,
+    k_blend_bwd2<true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.ids, gv.rec, bg, W, H, gx, iv.final_T,
                                                       iv.n_contrib, dL_dout, dacc);
   else if (ver == 2)
-    k_blend_bwd2<false><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, iv.final_T,
+    k_blend_bwd2<false><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.ids, gv.rec, bg, W, H, gx, iv.final_T,
                                                        iv.n_contrib, dL_dout, dacc);
   else
-    k_blend_bwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, bg, W, H, gx, iv.final_T, iv.n_contrib,
+    k_blend_bwd<<<gx * gy, kThreads, 0, st>>>(bv.ranges, bv.ids, gv.rec, bg, W, H, gx, iv.final_T, iv.n_contrib,
                                               dL_dout, dacc);
   GSB_CUDA(cudaGetLastError());
   return GSB_OK;
@@ -720,10 +772,10 @@ extern "C" GSB_API int gsb_blend_stats(const GsbCamera* cam, int32_t P, void* ge
   BinView bv = bin_view(binning, R, W, H);
   ImgView iv = img_view(image, W, H);
   GSB_CUDA(cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), st));
-  k_blend_fwd2<true, true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, out_color,
+  k_blend_fwd2<true, true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.ids, gv.rec, cam->bg, W, H, gx, out_color,
                                                           iv.final_T, iv.n_contrib, stats);
   if (dL_dout)
-    k_blend_bwd2<true, true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.s0, bv.s1, bv.s2, cam->bg, W, H, gx, iv.final_T,
+    k_blend_bwd2<true, true><<<gx * gy, kThreads2, 0, st>>>(bv.ranges, bv.ids, gv.rec, cam->bg, W, H, gx, iv.final_T,
                                                             iv.n_contrib, dL_dout, (float*)gv.dacc, stats);
   GSB_CUDA(cudaGetLastError());
   return GSB_OK;

@@ -61,12 +61,11 @@ constexpr uint32_t kSmallList = 2048, kLargeList = 8192;
 // ---- geom: P-sized scratch + per-tile counters (caller-owned, gsb_geom_bytes) -------------
 struct GeomView {
   CamConst* cam;
-  float4* xyAB;        // x, y, conic A, conic B
-  float4* Codq;        // conic C, opacity, depth, cull threshold
-  float4* rgbr;        // r, g, b, radius
-  uint2* rect;         // x: rx0 | rx1<<16   y: ry0 | ry1<<16
+  float4* rec;         // [4P] one 64-byte splat record per Gaussian (the blend kernels gather rows 0..2 by id):
+                       //   [0] x, y, A', B'      [1] C', opacity, cull threshold', id (bits)      (conic in the log2 domain:
+                       //   [2] r, g, b, radius                                                     power*log2e = A'dx^2+B'dxdy+C'dy^2)
+                       //   [3] depth, rect x (rx0 | rx1<<16), rect y (ry0 | ry1<<16), keep mask (bits)
   uint32_t* tiles;     // tile instances per Gaussian (after culling)
-  uint32_t* kmask;     // keep mask over the tile rect (rects of <= kCoopTiles tiles)
   uint8_t* clamped;
   float4* dacc;        // [3P] backward accumulators
   float* pose_part;    // [nblocks*16]
@@ -87,12 +86,8 @@ static inline GeomView geom_view(void* base, int P) {
   size_t Pp = (size_t)(P > 0 ? P : 1);
   auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += align_up(bytes); return r; };
   v.cam = (CamConst*)take(sizeof(CamConst));
-  v.xyAB = (float4*)take(Pp * 16);
-  v.Codq = (float4*)take(Pp * 16);
-  v.rgbr = (float4*)take(Pp * 16);
-  v.rect = (uint2*)take(Pp * 8);
+  v.rec = (float4*)take(Pp * 64);
   v.tiles = (uint32_t*)take(Pp * 4);
-  v.kmask = (uint32_t*)take(Pp * 4);
   v.clamped = (uint8_t*)take(Pp);
   v.dacc = (float4*)take(Pp * 48);
   size_t nb = (Pp + kPT - 1) / kPT;
@@ -111,9 +106,7 @@ static inline GeomView geom_view(void* base, int P) {
 // ---- binning: capacity-sized scratch (caller-owned, gsb_binning_bytes) --------------------
 struct BinView {
   unsigned long long* pairs;   // [cap] (depth bits << 32 | Gaussian id), unsorted per-tile segments
-  float4* s0;                  // x, y, A', B'        } per-tile slabs in (depth, id) order;
-  float4* s1;                  // C', opacity, cull threshold', gaussian id (bits)    } conic in the log2 domain
-  float4* s2;                  // r, g, b, -
+  uint32_t* ids;               // [cap + 8] Gaussian ids, per tile in (depth, id) order (what the blend kernels walk)
   uint2* ranges;               // [tiles]
   size_t total;
 };
@@ -126,9 +119,7 @@ static inline BinView bin_view(void* base, int64_t cap, int W, int H) {
   int ntiles = ((W + kBlock - 1) / kBlock) * ((H + kBlock - 1) / kBlock);
   auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += align_up(bytes); return r; };
   v.pairs = (unsigned long long*)take(Rp * 8);
-  v.s0 = (float4*)take(Rp * 16);
-  v.s1 = (float4*)take(Rp * 16);
-  v.s2 = (float4*)take(Rp * 16);
+  v.ids = (uint32_t*)take((Rp + 8) * 4);       // + 8: bulk copies of id chunks are rounded to 16 bytes
   v.ranges = (uint2*)take((size_t)ntiles * 8);
   v.total = off;
   return v;
@@ -157,8 +148,8 @@ int gsb_launch_tile_scan(const gsb::GeomView& gv, int ntiles, cudaStream_t st);
 // scatter + per-tile (depth, id) sort + slab gather + ranges; cap = instance capacity of the binning buffer
 int gsb_launch_binning(int P, const gsb::GeomView& gv, const gsb::BinView& bv, int W, int H, int exact_cull,
                        uint32_t cap, cudaStream_t st);
-int gsb_launch_blend_fwd(const gsb::BinView& bv, const gsb::ImgView& iv, const float* bg, int W, int H,
+int gsb_launch_blend_fwd(const gsb::GeomView& gv, const gsb::BinView& bv, const gsb::ImgView& iv, const float* bg, int W, int H,
                          float* out_color, cudaStream_t st);
 // pose_only: 8-value accumulator layout (dacc[5] = dL/db, no dL/dopacity), see k_blend_bwd2
-int gsb_launch_blend_bwd(const gsb::BinView& bv, const gsb::ImgView& iv, const float* bg, int W, int H,
+int gsb_launch_blend_bwd(const gsb::GeomView& gv, const gsb::BinView& bv, const gsb::ImgView& iv, const float* bg, int W, int H,
                          const float* dL_dout, float* dacc, bool pose_only, cudaStream_t st);

@@ -93,6 +93,7 @@ extern "C" GSB_API int gsb_set_option(const char* name, int value) {
 }
 extern "C" GSB_API int gsb_abi_version(void) { return 2; }
 
+constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kRowPad = 49;      // shared-memory SH row stride (48 + 1, conflict-free)
 
 extern "C" GSB_API size_t gsb_geom_bytes(int32_t P) { return geom_view(nullptr, P).total; }
@@ -361,7 +362,11 @@ k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
       p.rgb[0] = in.colors[3 * i]; p.rgb[1] = in.colors[3 * i + 1]; p.rgb[2] = in.colors[3 * i + 2];
     }
     qthr = cull_threshold(p.opacity);
-    sr_.x = p.x; sr_.y = p.y; sr_.A = p.A; sr_.B = p.B; sr_.C = p.C; sr_.qthr = qthr;
+    // The tile coverage is decided on the record exactly as it is stored (conic and threshold in the log2 domain), so
+    // that k_scatter -- which re-walks large rects from the stored record -- sees bit-identical inputs.
+    sr_.x = p.x; sr_.y = p.y;
+    sr_.A = 0.5f * kLog2e * p.A; sr_.B = 0.5f * kLog2e * p.B; sr_.C = 0.5f * kLog2e * p.C;
+    sr_.qthr = qthr < 0.f ? -1.f : 0.5f * kLog2e * qthr;
     sr_.rx0 = p.rx0; sr_.rx1 = p.rx1; sr_.ry0 = p.ry0; sr_.ry1 = p.ry1;
     const int area = (p.rx1 - p.rx0) * (p.ry1 - p.ry0);
     if (cull && qthr < 0.f) ntiles = 0;
@@ -380,12 +385,14 @@ k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
     if (coop) ntiles = c;
   }
   if (!active) return;
-  gv.xyAB[i] = make_float4(p.x, p.y, p.A, p.B);
-  gv.Codq[i] = make_float4(p.C, p.opacity, p.depth, qthr);
-  gv.rgbr[i] = make_float4(p.rgb[0], p.rgb[1], p.rgb[2], (float)p.radius);
-  gv.rect[i] = make_uint2((uint32_t)p.rx0 | ((uint32_t)p.rx1 << 16), (uint32_t)p.ry0 | ((uint32_t)p.ry1 << 16));
+  // the 64-byte splat record (conic pre-scaled into the log2 domain: power*log2(e) = A' dx^2 + B' dx dy + C' dy^2)
+  float4* rec = gv.rec + 4 * (size_t)i;
+  rec[0] = make_float4(p.x, p.y, -0.5f * kLog2e * p.A, -kLog2e * p.B);
+  rec[1] = make_float4(-0.5f * kLog2e * p.C, p.opacity, 0.5f * kLog2e * qthr, __uint_as_float((uint32_t)i));
+  rec[2] = make_float4(p.rgb[0], p.rgb[1], p.rgb[2], (float)p.radius);
+  rec[3] = make_float4(p.depth, __uint_as_float((uint32_t)p.rx0 | ((uint32_t)p.rx1 << 16)),
+                       __uint_as_float((uint32_t)p.ry0 | ((uint32_t)p.ry1 << 16)), __uint_as_float(kmask));
   gv.tiles[i] = ntiles;
-  gv.kmask[i] = kmask;
   gv.clamped[i] = (uint8_t)p.clamped;
   radii[i] = p.radius;
 }
@@ -648,7 +655,7 @@ extern "C" GSB_API int gsb_render(const GsbCamera* cam, int32_t P, void* geom, v
   ImgView iv = img_view(image, W, H);
   int rc = gsb_launch_binning(P, gv, bv, W, H, cam->exact_cull, (uint32_t)R, st);
   if (rc) return rc;
-  rc = gsb_launch_blend_fwd(bv, iv, cam->bg, W, H, out_color, st);
+  rc = gsb_launch_blend_fwd(gv, bv, iv, cam->bg, W, H, out_color, st);
   if (rc) return rc;
   if (status_host) GSB_CUDA(cudaMemcpyAsync(status_host, gv.status, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   GSB_CUDA(cudaGetLastError());
@@ -679,7 +686,7 @@ extern "C" GSB_API int gsb_backward(const GsbCamera* cam, const GsbGaussians* g,
                          !grads->dL_drotations && !grads->dL_dopacities && !grads->dL_dsh_dc && !grads->dL_dsh_rest &&
                          !grads->dL_dcolors && !grads->dL_dcov3D && gsb_option_blend_version() == 2 &&
                          gsb_option_stage_bulk() == 1;
-  rc = gsb_launch_blend_bwd(bv, iv, cam->bg, W, H, dL_dout, (float*)gv.dacc, pose_only, st);
+  rc = gsb_launch_blend_bwd(gv, bv, iv, cam->bg, W, H, dL_dout, (float*)gv.dacc, pose_only, st);
   if (rc) return rc;
   OutPtrs out;
   out.dmeans = grads->dL_dmeans3D; out.dmeans2D = grads->dL_dmeans2D; out.dscales = grads->dL_dscales;

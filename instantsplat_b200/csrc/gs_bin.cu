@@ -122,13 +122,13 @@ k_scatter(int P, GeomView gv, BinView bv, int W, int H, int gx, int exact_cull, 
   TileSink sink{gv.tcount, gv.tstart, gv.tcursor, bv.pairs, cap};
   uint32_t mask = 0u;
   if (n) {
-    const float4 r3 = gv.rec[4 * (size_t)i + 3];             // depth, rect x, rect y, keep mask
+    const float4 r3 = gv.brec[i];                            // depth, rect x, rect y, keep mask
     const uint32_t rcx = __float_as_uint(r3.y), rcy = __float_as_uint(r3.z);
     p.rx0 = rcx & 0xFFFF; p.rx1 = rcx >> 16; p.ry0 = rcy & 0xFFFF; p.ry1 = rcy >> 16;
     key = ((unsigned long long)__float_as_uint(r3.x) << 32) | (unsigned long long)(uint32_t)i;
     coop = (p.rx1 - p.rx0) * (p.ry1 - p.ry0) > kCoopTiles;
     if (coop) {                                              // re-walk the rect from the stored record (log2 domain)
-      const float4 e0 = gv.rec[4 * (size_t)i], e1 = gv.rec[4 * (size_t)i + 1];
+      const float4 e0 = gv.rec[3 * (size_t)i], e1 = gv.rec[3 * (size_t)i + 1];
       p.x = e0.x; p.y = e0.y; p.A = -e0.z; p.B = -0.5f * e0.w; p.C = -e1.x; p.qthr = e1.z;
     } else {
       mask = __float_as_uint(r3.w);                          // exactly the tiles k_preprocess counted

@@ -87,7 +87,7 @@ k_blend_fwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ ids, 
   for (int base = 0; base < n; base += kChunk1) {
     const int cnt = min(kChunk1, n - base);
     if ((int)threadIdx.x < cnt) {
-      const float4* r = rec + 4 * (size_t)ids[(size_t)rg.x + base + threadIdx.x];
+      const float4* r = rec + 3 * (size_t)ids[(size_t)rg.x + base + threadIdx.x];
       sm0[threadIdx.x] = r[0];
       sm1[threadIdx.x] = r[1];
       sm2[threadIdx.x] = r[2];
@@ -249,7 +249,7 @@ k_blend_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ ids, 
     const int base = ch * kChunk1;
     const int cnt = min(kChunk1, bmax - base);
     if ((int)threadIdx.x < cnt) {
-      const float4* r = rec + 4 * (size_t)ids[(size_t)rg.x + base + threadIdx.x];
+      const float4* r = rec + 3 * (size_t)ids[(size_t)rg.x + base + threadIdx.x];
       sm0[threadIdx.x] = r[0];
       sm1[threadIdx.x] = r[1];
       sm2[threadIdx.x] = r[2];
@@ -410,12 +410,12 @@ struct Stager {
       waited = q + 1;
       const uint32_t* row = sid[q % 3] + (e & 3);
       for (int k = threadIdx.x; k < cnt; k += NT) {
-        const float4* r = rec + 4 * (size_t)row[k];
+        const float4* r = rec + 3 * (size_t)row[k];
         cp_async16(&st->s0[k], r); cp_async16(&st->s1[k], r + 1); cp_async16(&st->s2[k], r + 2);
       }
     } else {
       for (int k = threadIdx.x; k < cnt; k += NT) {
-        const float4* r = rec + 4 * (size_t)__ldg(ids + e + k);
+        const float4* r = rec + 3 * (size_t)__ldg(ids + e + k);
         cp_async16(&st->s0[k], r); cp_async16(&st->s1[k], r + 1); cp_async16(&st->s2[k], r + 2);
       }
     }

@@ -61,10 +61,10 @@ constexpr uint32_t kSmallList = 2048, kLargeList = 8192;
 // ---- geom: P-sized scratch + per-tile counters (caller-owned, gsb_geom_bytes) -------------
 struct GeomView {
   CamConst* cam;
-  float4* rec;         // [4P] one 64-byte splat record per Gaussian (the blend kernels gather rows 0..2 by id):
+  float4* rec;         // [3P] one 48-byte splat record per Gaussian, array of structures (the blend kernels gather it by id):
                        //   [0] x, y, A', B'      [1] C', opacity, cull threshold', id (bits)      (conic in the log2 domain:
                        //   [2] r, g, b, radius                                                     power*log2e = A'dx^2+B'dxdy+C'dy^2)
-                       //   [3] depth, rect x (rx0 | rx1<<16), rect y (ry0 | ry1<<16), keep mask (bits)
+  float4* brec;        // [P] binning record: depth, rect x (rx0 | rx1<<16), rect y (ry0 | ry1<<16), keep mask (bits)
   uint32_t* tiles;     // tile instances per Gaussian (after culling)
   uint8_t* clamped;
   float4* dacc;        // [3P] backward accumulators
@@ -86,7 +86,8 @@ static inline GeomView geom_view(void* base, int P) {
   size_t Pp = (size_t)(P > 0 ? P : 1);
   auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += align_up(bytes); return r; };
   v.cam = (CamConst*)take(sizeof(CamConst));
-  v.rec = (float4*)take(Pp * 64);
+  v.rec = (float4*)take(Pp * 48);
+  v.brec = (float4*)take(Pp * 16);
   v.tiles = (uint32_t*)take(Pp * 4);
   v.clamped = (uint8_t*)take(Pp);
   v.dacc = (float4*)take(Pp * 48);

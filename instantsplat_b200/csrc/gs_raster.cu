@@ -384,17 +384,25 @@ k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
     const uint32_t c = visit_tiles_coop(coop, sr_, cam->W, cam->H, cam->gx, cull, sink, 0ull);
     if (coop) ntiles = c;
   }
-  if (!active) return;
-  // the 64-byte splat record (conic pre-scaled into the log2 domain: power*log2(e) = A' dx^2 + B' dx dy + C' dy^2)
-  float4* rec = gv.rec + 4 * (size_t)i;
-  rec[0] = make_float4(p.x, p.y, -0.5f * kLog2e * p.A, -kLog2e * p.B);
-  rec[1] = make_float4(-0.5f * kLog2e * p.C, p.opacity, 0.5f * kLog2e * qthr, __uint_as_float((uint32_t)i));
-  rec[2] = make_float4(p.rgb[0], p.rgb[1], p.rgb[2], (float)p.radius);
-  rec[3] = make_float4(p.depth, __uint_as_float((uint32_t)p.rx0 | ((uint32_t)p.rx1 << 16)),
-                       __uint_as_float((uint32_t)p.ry0 | ((uint32_t)p.ry1 << 16)), __uint_as_float(kmask));
-  gv.tiles[i] = ntiles;
-  gv.clamped[i] = (uint8_t)p.clamped;
-  radii[i] = p.radius;
+  // ---- outputs.  The 48-byte splat record (rows x,y,A',B' | C',o,qthr',id | r,g,b,radius; conic pre-scaled into the log2
+  // domain: power*log2(e) = A' dx^2 + B' dx dy + C' dy^2) is what the blend kernels gather by id, so it is stored as an
+  // array of structures -- transposed through shared memory so that the CTA's 128 x 48 B leave as one contiguous block
+  // of 128-bit stores.  The binning record (depth, tile rect, keep mask) is a plain coalesced float4 array.
+  __syncthreads();                                   // every thread is done with the staged inputs: reuse `sm`
+  float4* sm4 = reinterpret_cast<float4*>(sm);
+  if (active) {
+    sm4[3 * t + 0] = make_float4(p.x, p.y, -0.5f * kLog2e * p.A, -kLog2e * p.B);
+    sm4[3 * t + 1] = make_float4(-0.5f * kLog2e * p.C, p.opacity, 0.5f * kLog2e * qthr, __uint_as_float((uint32_t)i));
+    sm4[3 * t + 2] = make_float4(p.rgb[0], p.rgb[1], p.rgb[2], (float)p.radius);
+    gv.brec[i] = make_float4(p.depth, __uint_as_float((uint32_t)p.rx0 | ((uint32_t)p.rx1 << 16)),
+                             __uint_as_float((uint32_t)p.ry0 | ((uint32_t)p.ry1 << 16)), __uint_as_float(kmask));
+    gv.tiles[i] = ntiles;
+    gv.clamped[i] = (uint8_t)p.clamped;
+    radii[i] = p.radius;
+  }
+  __syncthreads();
+  float4* dst4 = gv.rec + 3 * (size_t)first;
+  for (int k = threadIdx.x; k < 3 * nv; k += kPT) dst4[k] = sm4[k];
 }
 
 // ------------------------------------------------------------------------------------------

@@ -233,5 +233,8 @@ def test_graph_replay_matches_eager_and_survives_overflow():
         tr, l_ovf = run(use_graph, sabotage_at=7)
         assert tr.overflows == 1 and tr.opt_step == n
         assert max(abs(a - b) for a, b in zip(l_eager, l_ovf)) < 1e-5, (use_graph, l_eager, l_ovf)
-        d = float((tr.params - eager.params).abs().max())
-        assert d < 5e-3, d                           # same trajectory up to atomic-order noise through Adam
+        # same trajectory up to atomic-order noise (a last-bit difference of a near-zero gradient becomes a full Adam
+        # step of either sign, so individual parameters may differ by a few learning rates)
+        diff = (tr.params - eager.params).abs()
+        assert float((diff > 1e-3).float().mean()) < 2e-3 and float(diff.max()) < 0.3, \
+            (float(diff.max()), float((diff > 1e-3).float().mean()))

@@ -24,10 +24,10 @@ constexpr float kLn2 = 0.6931471805599453f;
 #define GSB_CHUNK 224
 #endif
 #ifndef GSB_FWD_MINB
-#define GSB_FWD_MINB 7
+#define GSB_FWD_MINB 8
 #endif
 #ifndef GSB_BWD_MINB
-#define GSB_BWD_MINB 6
+#define GSB_BWD_MINB 8
 #endif
 constexpr int kChunk1 = 256;           // v1 blend kernels: one entry per thread
 constexpr int kChunk = GSB_CHUNK;      // slab entries staged per step in the blend kernels

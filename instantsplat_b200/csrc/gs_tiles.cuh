@@ -133,16 +133,40 @@ __device__ __forceinline__ uint32_t visit_tiles_coop(bool mine, const SplatRect&
     const unsigned long long bkey = __shfl_sync(0xffffffffu, key, src);
     const int w = b.rx1 - b.rx0, n = w * (b.ry1 - b.ry0);
     uint32_t run = 0;
-    for (int base = 0; base < n; base += 32) {
-      const int i = base + lane;
-      bool keep = false;
-      int tx = 0, ty = 0;
-      if (i < n) {
-        ty = b.ry0 + i / w; tx = b.rx0 + i - (i / w) * w;
-        keep = tile_kept(b, tx, ty, W, H, cull);
+    // kU x 32 tiles per trip, and within a trip every atomic is issued before the first result is consumed: a
+    // Gaussian that has grown over the whole frame (thousands of tiles) is a serial chain of trips for ONE warp, so the
+    // length of a trip -- one atomic round trip instead of kU -- is the tail of the whole kernel
+    constexpr int kU = 4;
+    for (int base = 0; base < n; base += 32 * kU) {
+      bool keep[kU];
+      uint32_t tile[kU], pos[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = base + u * 32 + lane;
+        keep[u] = false;
+        tile[u] = 0u;
+        if (i < n) {
+          const int ty = b.ry0 + i / w, tx = b.rx0 + i - (i / w) * w;
+          keep[u] = tile_kept(b, tx, ty, W, H, cull);
+          tile[u] = (uint32_t)(ty * gx + tx);
+        }
       }
-      if (keep) sink_tile(s, (uint32_t)(ty * gx + tx), bkey);
-      run += __popc(__ballot_sync(0xffffffffu, keep));
+      if (s.pairs) {
+#pragma unroll
+        for (int u = 0; u < kU; ++u) pos[u] = keep[u] ? atomicAdd(s.tcursor + tile[u], 1u) : 0xFFFFFFFFu;
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          if (keep[u] && pos[u] < s.tcount[tile[u]]) {
+            const uint32_t dst = s.tstart[tile[u]] + pos[u];
+            if (dst < s.cap) s.pairs[dst] = bkey;
+          }
+      } else {
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          if (keep[u]) atomicAdd(s.tcount + tile[u], 1u);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) run += __popc(__ballot_sync(0xffffffffu, keep[u]));
     }
     if (lane == src) result = run;
   }

@@ -22,6 +22,13 @@ def launch_adam(entries, flags, skip_ptr=None, step_sizes_dev=None):
     if step_sizes_dev is not None and len(entries) > ADAM_MAX_TENSORS:
         raise _lib.GsbError("device-side step sizes support at most one launch (8 tensors)")
     L = _lib.lib()
+    if not entries:
+        return
+    with torch.cuda.device(entries[0]["param"].device):       # launch on the tensors' device, whatever is current
+        _launch_adam_on_device(L, entries, flags, skip_ptr, step_sizes_dev)
+
+
+def _launch_adam_on_device(L, entries, flags, skip_ptr, step_sizes_dev):
     for i in range(0, len(entries), ADAM_MAX_TENSORS):
         chunk = entries[i:i + ADAM_MAX_TENSORS]
         arr = (GsbAdamTensor * len(chunk))()

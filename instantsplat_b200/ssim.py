@@ -18,10 +18,11 @@ class _FusedSSIM(torch.autograd.Function):
         if a.dim() != 4 or a.shape != b.shape:
             raise RuntimeError("fused_ssim expects two [B,C,H,W] tensors of the same shape")
         B, C, H, W = a.shape
-        sums = torch.zeros(2, dtype=torch.float64, device=a.device)
-        maps = torch.empty((3, B, C, H, W), dtype=torch.float32, device=a.device) if train else None
-        check(L.gsb_ssim_forward(B * C, H, W, a.data_ptr(), b.data_ptr(), sums.data_ptr(),
-                                 None if maps is None else maps.data_ptr(), _lib.stream_ptr()), "gsb_ssim_forward")
+        with torch.cuda.device(a.device):
+            sums = torch.zeros(2, dtype=torch.float64, device=a.device)
+            maps = torch.empty((3, B, C, H, W), dtype=torch.float32, device=a.device) if train else None
+            check(L.gsb_ssim_forward(B * C, H, W, a.data_ptr(), b.data_ptr(), sums.data_ptr(),
+                                     None if maps is None else maps.data_ptr(), _lib.stream_ptr()), "gsb_ssim_forward")
         ctx.save_for_backward(a, b, maps)
         ctx.n = B * C * H * W
         return (sums[1] / ctx.n).float()
@@ -32,11 +33,12 @@ class _FusedSSIM(torch.autograd.Function):
         if maps is None:
             raise RuntimeError("fused_ssim(train=False) cannot be differentiated")
         B, C, H, W = a.shape
-        out = torch.empty_like(a)
-        g = f32c(grad).reshape(1)
-        check(_lib.lib().gsb_ssim_backward(B * C, H, W, a.data_ptr(), b.data_ptr(), maps.data_ptr(),
-                                           1.0 / ctx.n, g.data_ptr(), out.data_ptr(), _lib.stream_ptr()),
-              "gsb_ssim_backward")
+        with torch.cuda.device(a.device):
+            out = torch.empty_like(a)
+            g = f32c(grad).reshape(1)
+            check(_lib.lib().gsb_ssim_backward(B * C, H, W, a.data_ptr(), b.data_ptr(), maps.data_ptr(),
+                                               1.0 / ctx.n, g.data_ptr(), out.data_ptr(), _lib.stream_ptr()),
+                  "gsb_ssim_backward")
         return out, None, None
 
 
@@ -54,10 +56,11 @@ class _FusedLoss(torch.autograd.Function):
         L = _lib.lib()
         a, b = f32c(image), f32c(gt)
         C, H, W = a.shape
-        sums = torch.zeros(2, dtype=torch.float64, device=a.device)
-        maps = torch.empty((3, C, H, W), dtype=torch.float32, device=a.device)
-        check(L.gsb_loss_forward(C, H, W, a.data_ptr(), b.data_ptr(), sums.data_ptr(), maps.data_ptr(),
-                                 _lib.stream_ptr()), "gsb_loss_forward")
+        with torch.cuda.device(a.device):
+            sums = torch.zeros(2, dtype=torch.float64, device=a.device)
+            maps = torch.empty((3, C, H, W), dtype=torch.float32, device=a.device)
+            check(L.gsb_loss_forward(C, H, W, a.data_ptr(), b.data_ptr(), sums.data_ptr(), maps.data_ptr(),
+                                     _lib.stream_ptr()), "gsb_loss_forward")
         ctx.save_for_backward(a, b, maps)
         ctx.lam = float(lambda_dssim)
         n = C * H * W
@@ -67,9 +70,10 @@ class _FusedLoss(torch.autograd.Function):
     def backward(ctx, grad):
         a, b, maps = ctx.saved_tensors
         C, H, W = a.shape
-        out = torch.empty_like(a)
-        check(_lib.lib().gsb_loss_backward(C, H, W, a.data_ptr(), b.data_ptr(), maps.data_ptr(), ctx.lam,
-                                           out.data_ptr(), _lib.stream_ptr()), "gsb_loss_backward")
+        with torch.cuda.device(a.device):
+            out = torch.empty_like(a)
+            check(_lib.lib().gsb_loss_backward(C, H, W, a.data_ptr(), b.data_ptr(), maps.data_ptr(), ctx.lam,
+                                               out.data_ptr(), _lib.stream_ptr()), "gsb_loss_backward")
         return out * grad, None, None
 
 

@@ -41,7 +41,10 @@ def parse():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink P (debug only; invalidates the number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--blend-version", type=int, default=0, help="debug: force blend kernel version 1|2|3")
-    ap.add_argument("--no-graph", action="store_true", help="single GPU: do not replay the iteration from CUDA graphs")
+    ap.add_argument("--graph", action="store_true",
+                    help="multi-GPU with --exchange fused_p2p: replay each rank's iteration (exchange included) from CUDA graphs")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="do not replay the iteration from CUDA graphs (single GPU, and multi-GPU with --exchange fused_p2p)")
     ap.add_argument("--exchange", default="fused_p2p", choices=["allreduce", "fused_p2p", "fused_p2p_nccl"],
                     help="multi-GPU gradient exchange: NCCL all-reduce + Adam, or the fused P2P "
                          "reduce-scatter->Adam->all-gather kernel (default)")
@@ -295,7 +298,11 @@ def run_b200(args):
     del tgt
     torch.cuda.empty_cache()
     gt_host = gt_dev.cpu().pin_memory()
-    use_graph = world == 1 and not args.no_graph
+    # N=1: graph replay is the default.  N>1: capturable with the flag-barrier exchange and bit-exact
+    # (tests/test_multigpu.py "fused_p2p+graph"), but measured no faster than eager launches at N=2 (2.19 vs 2.13
+    # ms/step, profiles/r02_bench_n2_graph*.json): the host already runs ahead of a step that waits on its peers, so
+    # eager stays the default there and --graph opts in
+    use_graph = (world == 1 and not args.no_graph) or (world > 1 and args.graph and args.exchange == "fused_p2p")
     tr = I.JointTrainer(sc, dev, gt_images=gt_dev, world_size=world, rank=rank, exchange=args.exchange,
                         use_graph=use_graph)
     # ---- e2e pipeline through the public API: this step's GT image is copied H2D from pinned memory on a copy
@@ -359,7 +366,8 @@ def run_b200(args):
 
     W_, K = max(3, args.warmup), args.steps
     if use_graph:
-        W_ = max(W_, 2 * sc.n_views + 2)      # first visit of a view is eager, the second captures its graph
+        # first visit of a view is eager, the second captures its graph (a rank visits ceil(n_views / world) views)
+        W_ = max(W_, 2 * ((sc.n_views + world - 1) // world) + 2)
     for s in range(W_):
         device_step(s)
     sampler = ClockSampler(local)
@@ -393,9 +401,13 @@ def run_b200(args):
         L.gsb_profile_enable(0)
         clocks = sampler.stop() if rank == 0 else None
         ms_prof, Kp = ms_dev, K
-    for s in range(2):
+    # e2e through JointTrainer.step(view, gt=<staging buffer>): graphs are keyed on (view, staging buffer), so warm
+    # up until every pair this rank will visit has been captured
+    tr.use_graph = use_graph
+    n_e2e_warm = 2 * ((sc.n_views + world - 1) // world) + 2 if use_graph else 2
+    for s in range(n_e2e_warm):
         e2e_step(W_ + K + s)
-    ms_e2e = timed(e2e_step, K, W_ + K + 2)
+    ms_e2e = timed(e2e_step, K, W_ + K + n_e2e_warm)
     # ---- the same iteration through the reference's own operator API (boundaries B1-B4): the loop body of
     # /root/reference/train.py:140-211 transcribed onto the repo's mirror of GaussianModel (the GPU box has no
     # /root/reference; tests/test_reference_shims_cpu.py runs the real reference modules on the same interfaces).

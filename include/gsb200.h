@@ -203,7 +203,9 @@ GSB_API int gsb_ipc_free(void* dev_ptr);
 /* Flag barrier / small exchange over peer memory (replace the tiny NCCL collectives around the fused kernel).
  * peer_signal: host array of `world` device pointers to every rank's signal buffer (gsb_peer_signal_bytes() bytes,
  * allocated zeroed with gsb_ipc_alloc, own rank included).  epoch: the optimizer step, 1, 2, 3, ... (same on all
- * ranks).  gsb_peer_exchange (channel 0): flags8[0..6] gate flags, overflow_word (device, may be NULL) and
+ * ranks); epoch 0 = use the device-resident epoch (word 61 of the local signal buffer, advanced by every
+ * gsb_peer_exchange and re-used by the gsb_peer_barrier of the same step), which makes both launches replayable from a
+ * CUDA graph.  Do not mix the two conventions on one signal buffer.  gsb_peer_exchange (channel 0): flags8[0..6] gate flags, overflow_word (device, may be NULL) and
  * pose_grad[n_pose] are replaced IN PLACE by their sums over the ranks (flags8[7] = number of ranks whose
  * overflow_word was set); it is also the barrier "every rank's gradients are written".  gsb_peer_barrier: pure
  * barrier on `channel` (use 1 after the fused kernel: "every rank's parameter stores have landed").  A wait that
@@ -229,7 +231,9 @@ typedef struct GsbShardPiece { /* (one tensor's segment) intersected with (this 
   double step_size, beta1, beta2, eps;
 } GsbShardPiece;
 
-/* skip_if_nonzero (device, may be NULL): when the word is non-zero the kernel returns without touching anything
+/* step_sizes_dev (device, may be NULL): float[GSB_ADAM_MAX_TENSORS], entry flag_index replaces the piece's step_size
+ * (CUDA-graph replay: the host refreshes the array before every replay).
+ * skip_if_nonzero (device, may be NULL): when the word is non-zero the kernel returns without touching anything
  * (the sum over ranks of the forward's overflow words, so every replica takes the same decision).
  * peer_grads / peer_params: host arrays of `world` device pointers to every rank's flat gradient / parameter
  * buffer (own rank included).  exp_avg / exp_avg_sq: this rank's shard only, indexed by (element - shard_begin). */
@@ -237,7 +241,7 @@ GSB_API int gsb_fused_rs_adam_ag(int32_t world, int32_t rank, const float* const
                                  float* const* peer_params, float* exp_avg_shard, float* exp_avg_sq_shard,
                                  int64_t shard_begin, int32_t n_pieces, const GsbShardPiece* pieces,
                                  const uint32_t* flags, const uint32_t* skip_if_nonzero, float grad_scale,
-                                 gsb_stream_t stream);
+                                 const float* step_sizes_dev, gsb_stream_t stream);
 
 /* simple_knn._C.distCUDA2 (scene/gaussian_model.py:20,156-160; init only):
  * out[i] = mean squared distance from point i to its 3 nearest neighbours (exact).  points [P,3], out [P]. */

@@ -142,7 +142,7 @@ def lib() -> ctypes.CDLL:
     L.gsb_ipc_close.argtypes = [vp]
     L.gsb_ipc_free.argtypes = [vp]
     L.gsb_fused_rs_adam_ag.argtypes = [i32, i32, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp, i64, i32,
-                                       ctypes.POINTER(GsbShardPiece), vp, vp, ctypes.c_float, vp]
+                                       ctypes.POINTER(GsbShardPiece), vp, vp, ctypes.c_float, vp, vp]
     L.gsb_knn_scratch_bytes.argtypes = [i32]
     L.gsb_knn_scratch_bytes.restype = sz
     L.gsb_knn_mean_dist2.argtypes = [i32, vp, vp, vp, sz, vp]

@@ -40,6 +40,7 @@ struct Piece {
   unsigned int first_block, nblocks;
 };
 struct FusedArgs {
+  const float* step_dev;     // optional [GSB_ADAM_MAX_TENSORS]: step size per flag_index (CUDA-graph replay)
   int world, rank, n_pieces;
   long long shard_begin;
   float gscale;
@@ -65,13 +66,14 @@ __device__ __forceinline__ void st_peer(float* p, const float4& v) {
                "f"(v.w) : "memory");
 }
 
-__device__ __forceinline__ void adam1(const Piece& t, bool gate, float lr_mul, float& p, float g, float& m, float& v) {
+__device__ __forceinline__ void adam1(const Piece& t, float step, bool gate, float lr_mul, float& p, float g, float& m,
+                                      float& v) {
   if (gate) {
     m = __fadd_rn(__fmul_rn(m, t.b1), __fmul_rn(g, t.omb1));
     v = __fadd_rn(__fmul_rn(v, t.b2), __fmul_rn(__fmul_rn(t.omb2, g), g));
   }
   float denom = __fadd_rn(__fsqrt_rn(v), t.eps);
-  p = __fadd_rn(p, __fmul_rn(-(t.step * lr_mul), __fdiv_rn(m, denom)));
+  p = __fadd_rn(p, __fmul_rn(-(step * lr_mul), __fdiv_rn(m, denom)));
 }
 
 template <int WORLD>
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(kFT) k_fused_rs_adam_ag(FusedArgs a, const uns
     if (i < a.n_pieces && blockIdx.x >= a.pc[i].first_block) k = i;
   const Piece& t = a.pc[k];
   const bool gate = flags[t.flag_index] != 0;
+  const float step = a.step_dev ? a.step_dev[t.flag_index] : t.step;
   const long long base = t.begin + (long long)(blockIdx.x - t.first_block) * kElemsPerBlock;
 #pragma unroll
   for (int u = 0; u < kVecPerThread; ++u) {
@@ -106,10 +109,10 @@ __global__ void __launch_bounds__(kFT) k_fused_rs_adam_ag(FusedArgs a, const uns
       l0 = __ldg(t.ppl + q / t.row_len); l1 = __ldg(t.ppl + (q + 1) / t.row_len);
       l2 = __ldg(t.ppl + (q + 2) / t.row_len); l3 = __ldg(t.ppl + (q + 3) / t.row_len);
     }
-    adam1(t, gate, l0, p.x, s.x, m.x, v.x);
-    adam1(t, gate, l1, p.y, s.y, m.y, v.y);
-    adam1(t, gate, l2, p.z, s.z, m.z, v.z);
-    adam1(t, gate, l3, p.w, s.w, m.w, v.w);
+    adam1(t, step, gate, l0, p.x, s.x, m.x, v.x);
+    adam1(t, step, gate, l1, p.y, s.y, m.y, v.y);
+    adam1(t, step, gate, l2, p.z, s.z, m.z, v.z);
+    adam1(t, step, gate, l3, p.w, s.w, m.w, v.w);
     *reinterpret_cast<float4*>(a.m + le) = m;
     *reinterpret_cast<float4*>(a.v + le) = v;
 #pragma unroll
@@ -148,8 +151,25 @@ __device__ __forceinline__ void st_relaxed_sys_f32(float* p, float v) {
 
 struct SigArgs { int world, rank; unsigned int epoch; int channel; unsigned int* sig[kMaxWorld]; };
 
+// epoch == 0 in the arguments means "device-resident epoch": word 61 of the local signal buffer, advanced by every
+// k_peer_exchange (once per optimizer step on every rank, so the ranks stay in lockstep) and re-used by the
+// k_peer_barrier of the same step.  That makes both launches replayable from a CUDA graph (frozen arguments).
+__device__ __forceinline__ unsigned int resolve_epoch(const SigArgs& a, bool advance) {
+  __shared__ unsigned int s_epoch;
+  if (a.epoch != 0u) return a.epoch;
+  if (threadIdx.x == 0) {
+    unsigned int e = a.sig[a.rank][61];
+    if (advance) { e += 1u; if (e == 0u) e = 1u; a.sig[a.rank][61] = e; }
+    s_epoch = e;
+  }
+  __syncthreads();
+  return s_epoch;
+}
+
 // all threads of the (single) CTA call this; returns after every rank has signalled `epoch` on `channel`
-__device__ __forceinline__ void signal_and_wait(const SigArgs& a) {
+__device__ __forceinline__ void signal_and_wait(const SigArgs& a0, unsigned int epoch) {
+  SigArgs a = a0;
+  a.epoch = epoch;
   const int par = (int)(a.epoch & 1u);
   __syncthreads();
   if ((int)threadIdx.x < a.world) {
@@ -164,14 +184,15 @@ __device__ __forceinline__ void signal_and_wait(const SigArgs& a) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_peer_barrier(SigArgs a) { signal_and_wait(a); }
+__global__ void __launch_bounds__(256) k_peer_barrier(SigArgs a) { signal_and_wait(a, resolve_epoch(a, false)); }
 
 // flags [8] uint32 (this rank's gate flags; slot 7 is overwritten with *ovf), pose_grad [n_pose] floats: every rank
 // ends up with the SUM over ranks of both, in place, accumulated in rank order (identical on all ranks).
 __global__ void __launch_bounds__(256) k_peer_exchange(SigArgs a, unsigned int* flags, const unsigned int* ovf,
                                                        float* pose_grad, int n_pose) {
   const int n = 8 + n_pose;
-  const int par = (int)(a.epoch & 1u);
+  const unsigned int epoch = resolve_epoch(a, true);
+  const int par = (int)(epoch & 1u);
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     float v;
     if (t < 7) v = (float)flags[t];
@@ -180,7 +201,7 @@ __global__ void __launch_bounds__(256) k_peer_exchange(SigArgs a, unsigned int* 
     for (int p = 0; p < a.world; ++p)
       st_relaxed_sys_f32(reinterpret_cast<float*>(a.sig[p] + 64) + ((size_t)par * kMaxWorld + a.rank) * kXchMax + t, v);
   }
-  signal_and_wait(a);
+  signal_and_wait(a, epoch);
   const float* mine = reinterpret_cast<const float*>(a.sig[a.rank] + 64) + (size_t)par * kMaxWorld * kXchMax;
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     float s = 0.f;
@@ -236,7 +257,7 @@ extern "C" GSB_API int gsb_fused_rs_adam_ag(int32_t world, int32_t rank, const f
                                             float* const* peer_params, float* exp_avg_shard, float* exp_avg_sq_shard,
                                             int64_t shard_begin, int32_t n_pieces, const GsbShardPiece* pieces,
                                             const uint32_t* flags, const uint32_t* skip_if_nonzero, float grad_scale,
-                                            gsb_stream_t stream_) {
+                                            const float* step_sizes_dev, gsb_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || !peer_grads || !peer_params || !exp_avg_shard ||
       !exp_avg_sq_shard || n_pieces < 0 || n_pieces > kMaxPieces || (n_pieces > 0 && !pieces) || !flags ||
@@ -247,6 +268,7 @@ extern "C" GSB_API int gsb_fused_rs_adam_ag(int32_t world, int32_t rank, const f
   FusedArgs a;
   memset(&a, 0, sizeof(a));
   a.world = world; a.rank = rank; a.n_pieces = n_pieces; a.shard_begin = shard_begin; a.gscale = grad_scale;
+  a.step_dev = step_sizes_dev;
   a.m = exp_avg_shard; a.v = exp_avg_sq_shard;
   for (int r = 0; r < world; ++r) {
     if (!peer_grads[r] || !peer_params[r] || (((uintptr_t)peer_grads[r] | (uintptr_t)peer_params[r]) & 15)) {
@@ -291,7 +313,7 @@ extern "C" GSB_API int gsb_fused_rs_adam_ag(int32_t world, int32_t rank, const f
 }
 
 static int make_sig(int32_t world, int32_t rank, void* const* sig, uint32_t epoch, int channel, SigArgs& a) {
-  if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || !sig || channel < 0 || channel > 1 || epoch == 0) {
+  if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world || !sig || channel < 0 || channel > 1) {
     gsb_set_error("gsb_peer_*: bad argument");
     return GSB_ERR_INVALID;
   }

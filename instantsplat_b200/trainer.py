@@ -112,7 +112,6 @@ class JointTrainer:
             self.exp_avg_sq = torch.zeros(n_sh, dtype=torch.float32, device=self.dev)
             self._sync = torch.zeros(1, dtype=torch.float32, device=self.dev)
             self._xch = torch.zeros(8 + scene.n_views * 7, dtype=torch.float32, device=self.dev)
-            self._epoch = 0
             if self.exchange == "fused_p2p":
                 self._peer_sig = PeerBuffer(L_sig_words(), self.dev, process_group)
         else:
@@ -172,11 +171,14 @@ class JointTrainer:
         self._pose_flags = torch.zeros(8, dtype=torch.int32, device=self.dev)
         if world_size > 1:    # the word the optimizer kernels test: overflow flags summed over the ranks
             self._ovf = self.flags[7:8] if self._fused else self._pg_buf[-1:]
-        # CUDA-graph replay of the whole iteration (single GPU): one graph per (view, ground-truth buffer); everything
-        # that changes from step to step reaches the kernels through device memory (Adam step sizes) or is part of
-        # the graph's identity (view pose row, active SH degree, binning capacity)
-        self.use_graph = bool(use_graph) and world_size == 1
+        # CUDA-graph replay of the whole iteration: one graph per (view, ground-truth buffer); everything that changes
+        # from step to step reaches the kernels through device memory (Adam step sizes, the flag barriers' epoch) or is
+        # part of the graph's identity (view pose row, active SH degree, binning capacity).  Multi-GPU: only the
+        # "fused_p2p" exchange is capturable (its collectives are this library's own kernels over peer memory; every
+        # rank replays its own graph and the flag barriers inside keep the ranks in step).
+        self.use_graph = bool(use_graph) and (world_size == 1 or self.exchange == "fused_p2p")
         self._graphs = {}
+        self._after_backward = None   # test hook: called (and captured) between the backward and the optimizer step
         self._step_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self._step_dev = torch.zeros(8, dtype=torch.float32, device=self.dev)
         self._status_t.zero_()        # the forward serial number lives in these words
@@ -380,17 +382,20 @@ class JointTrainer:
         return dict(xyz=self.xyz_sched(self.iteration), f_dc=c.feature_lr * 10, f_rest=c.feature_lr / 20.0 * 10,
                     opacity=c.opacity_lr, scaling=c.scaling_lr * 10, rotation=c.rotation_lr * 10)
 
-    def fused_exchange_step(self) -> None:
-        """Multi-GPU: gate flags + pose gradients all-reduced (tiny NCCL collectives that double as the
-        pre-barrier), then ONE kernel per rank doing reduce-scatter -> per-point Adam -> all-gather over
-        NVLink peer memory (csrc/gs_comm.cu), then a barrier before anyone reads the new parameters."""
+    def fused_exchange_step(self, _advance: bool = True, _dev_steps: bool = False) -> None:
+        """Multi-GPU: gate flags + pose gradients summed over the ranks (one tiny kernel over peer memory, or a tiny
+        NCCL all-reduce; either doubles as the pre-barrier), then ONE kernel per rank doing reduce-scatter ->
+        per-point Adam -> all-gather over NVLink peer memory (csrc/gs_comm.cu), then a barrier before anyone reads
+        the new parameters.  _dev_steps: the kernels read their Adam step sizes from self._step_dev (graph replay)."""
         import torch.distributed as dist
         from ._lib import GsbAdamTensor, GsbShardPiece
         L = _lib.lib()
         st = _lib.stream_ptr()
         c = self.cfg
-        self.opt_step += 1
+        if _advance:
+            self.opt_step += 1
         t = self.opt_step
+        step_dev = self._step_dev if _dev_steps else None
         b1, b2, eps = 0.9, 0.999, 1e-15
         corr = (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
         lrs = self._lrs()
@@ -404,9 +409,9 @@ class JointTrainer:
         check(L.gsb_adam_gate(len(SEGMENTS), arr, self.flags.data_ptr(), st), "gsb_adam_gate")
         if self.exchange == "fused_p2p":
             # gate flags, the binning-overflow word and the pose-gradient table are summed over the ranks by ONE tiny
-            # kernel through peer memory; its flag barrier is also "every rank's gradients are written"
-            self._epoch += 1
-            check(L.gsb_peer_exchange(self.world_size, self.rank, self._peer_sig.ptr_array(), self._epoch,
+            # kernel through peer memory; its flag barrier is also "every rank's gradients are written".  Epoch 0 = the
+            # device-resident epoch counter (advanced by this kernel), so the launch is identical every step
+            check(L.gsb_peer_exchange(self.world_size, self.rank, self._peer_sig.ptr_array(), 0,
                                       self.flags.data_ptr(), self._status_dev + 4, self.pose_grad.data_ptr(),
                                       self.pose_grad.numel(), st), "gsb_peer_exchange")
         else:
@@ -434,16 +439,18 @@ class JointTrainer:
         check(L.gsb_fused_rs_adam_ag(self.world_size, self.rank, self._peer_grads.ptr_array(),
                                      self._peer_params.ptr_array(), self.exp_avg.data_ptr(),
                                      self.exp_avg_sq.data_ptr(), lo, len(pieces), parr, self.flags.data_ptr(),
-                                     self._ovf.data_ptr(), 1.0 / self.world_size, st), "gsb_fused_rs_adam_ag")
+                                     self._ovf.data_ptr(), 1.0 / self.world_size,
+                                     None if step_dev is None else step_dev.data_ptr(), st), "gsb_fused_rs_adam_ag")
         # 3. pose table: replicated Adam on the all-reduced pose gradients
         if c.optim_pose:
             launch_adam([dict(param=self.poses, grad=self.pose_grad, exp_avg=self.pose_m, exp_avg_sq=self.pose_v,
                               per_point_lr=None, row_len=7, step_size=self.cam_sched(self.iteration) * corr,
                               beta1=b1, beta2=b2, eps=eps, weight_decay=0.0, grad_scale=1.0 / self.world_size)],
-                        self._pose_flags, skip_ptr=self._ovf.data_ptr())
+                        self._pose_flags, skip_ptr=self._ovf.data_ptr(),
+                        step_sizes_dev=None if step_dev is None else step_dev[len(SEGMENTS):])
         # 4. nobody may start the next forward before every rank's parameter stores have landed
         if self.exchange == "fused_p2p":
-            check(L.gsb_peer_barrier(self.world_size, self.rank, self._peer_sig.ptr_array(), self._epoch, 1, st),
+            check(L.gsb_peer_barrier(self.world_size, self.rank, self._peer_sig.ptr_array(), 0, 1, st),
                   "gsb_peer_barrier")
         else:
             dist.all_reduce(self._sync, group=self.pg)
@@ -464,7 +471,11 @@ class JointTrainer:
                 with torch.cuda.graph(g):
                     self._launch_forward(view)
                     self.loss_and_backward(view, gt)
-                    if do_opt:
+                    if self._after_backward is not None:
+                        self._after_backward()
+                    if do_opt and self._fused:
+                        self.fused_exchange_step(_advance=False, _dev_steps=True)
+                    elif do_opt:
                         self.optimizer_step(_advance=False, _dev_steps=True)
                 self._graphs[key] = g
             self._fwd_count += 1
@@ -472,12 +483,18 @@ class JointTrainer:
             g.replay()
             if self._settle():
                 return
+            if self.world_size > 1:
+                raise _lib.GsbError(f"rank {self.rank}: {self.last_R} instances exceeded the binning capacity; the "
+                                    "optimizer update of this step was skipped on every rank (parameters are "
+                                    "consistent).  Raise JointTrainer.headroom.")
             # capacity exceeded: the device skipped the update, the buffer has been enlarged -> new graph, once more
         raise _lib.GsbError("graph replay: binning capacity exceeded twice in a row")
 
     def _run_iteration(self, view: int, gt: torch.Tensor, do_opt: bool) -> None:
         self._launch_forward(view)
         self.loss_and_backward(view, gt)
+        if self._after_backward is not None:
+            self._after_backward()
         if not do_opt:
             return
         if self._fused:

@@ -21,11 +21,21 @@ dev = torch.device("cuda", local)
 sc = surface_scene(20_000, 4, 256, 192, seed=9, sh_degree=3)
 gts = torch.rand(4, 3, sc.height, sc.width, generator=torch.Generator().manual_seed(2))
 mode = os.environ.get("GSB_TEST_MODE", "allreduce")
-N_STEPS = 3
-tr = I.JointTrainer(sc, dev, gt_images=gts, world_size=world, rank=rank, exchange=mode)
+graph = mode.endswith("+graph")          # the whole iteration incl. the exchange replayed from CUDA graphs
+mode = mode.replace("+graph", "")
+N_STEPS = 7 if graph else 3              # graph: step 0 eager (sizes the binning), then capture + replays per view
+tr = I.JointTrainer(sc, dev, gt_images=gts, world_size=world, rank=rank, exchange=mode, use_graph=graph)
+assert tr.use_graph == graph
 captured = []
+if graph:
+    last_g, last_pg = torch.zeros_like(tr.grads), torch.zeros_like(tr.pose_grad)
+    tr._after_backward = lambda: (last_g.copy_(tr.grads), last_pg.copy_(tr.pose_grad))
 for s in range(N_STEPS):
     v = view_for_step(sc.n_views, world, rank, s)
+    if graph:
+        tr.step(v)
+        captured.append((last_g.clone(), last_pg.clone()))
+        continue
     tr.iteration += world
     tr._launch_forward(v)
     tr.loss_and_backward(v, tr.gt[v])
@@ -38,6 +48,8 @@ for s in range(N_STEPS):
     assert tr._settle()
 torch.cuda.synchronize()
 tr.check_peer_errors()
+if graph:
+    assert len(tr._graphs) == len(set(view_for_step(sc.n_views, world, rank, s) for s in range(N_STEPS))), tr._graphs.keys()
 # every replica must hold identical parameters
 mine = tr.params.clone()
 ref0 = mine.clone()
@@ -74,7 +86,7 @@ if rank == 0:
     # the step must actually have moved the parameters
     moved = float((one.view(one.params, "xyz") - sc.params["xyz"].to(dev)).abs().max())
     assert moved > 0
-    print(f"MGPU_OK mode={mode} world={world} steps={N_STEPS} max param diff {diff:.1e} pose diff {perr:.1e}")
+    print(f"MGPU_OK mode={mode}{'+graph' if graph else ''} world={world} steps={N_STEPS} max param diff {diff:.1e} pose diff {perr:.1e}")
 dist.barrier()
 tr.close()
 dist.destroy_process_group()

@@ -126,8 +126,11 @@ k_scatter(int P, GeomView gv, BinView bv, int W, int H, int gx, int exact_cull, 
     const uint32_t rcx = __float_as_uint(r3.y), rcy = __float_as_uint(r3.z);
     p.rx0 = rcx & 0xFFFF; p.rx1 = rcx >> 16; p.ry0 = rcy & 0xFFFF; p.ry1 = rcy >> 16;
     key = ((unsigned long long)__float_as_uint(r3.x) << 32) | (unsigned long long)(uint32_t)i;
-    coop = (p.rx1 - p.rx0) * (p.ry1 - p.ry0) > kCoopTiles;
-    if (coop) {                                              // re-walk the rect from the stored record (log2 domain)
+    const int area = (p.rx1 - p.rx0) * (p.ry1 - p.ry0);
+    coop = area > kCoopTiles && area <= kBigRect;            // larger rects are emitted by k_big_rects
+    if (area > kBigRect) {
+      // nothing to do here
+    } else if (coop) {                                              // re-walk the rect from the stored record (log2 domain)
       const float4 e0 = gv.rec[3 * (size_t)i], e1 = gv.rec[3 * (size_t)i + 1];
       p.x = e0.x; p.y = e0.y; p.A = -e0.z; p.B = -0.5f * e0.w; p.C = -e1.x; p.qthr = e1.z;
     } else {
@@ -136,6 +139,89 @@ k_scatter(int P, GeomView gv, BinView bv, int W, int H, int gx, int exact_cull, 
   }
   warp_sink_masks(mask, p.rx0, p.ry0, p.rx1 - p.rx0, gx, sink, key);
   visit_tiles_coop(coop, p, W, H, gx, exact_cull != 0, sink, key);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// k_big_rects: Gaussians whose tile rect exceeds kBigRect tiles, flattened into (Gaussian, trip) work items
+// ------------------------------------------------------------------------------------------
+// k_preprocess only queues such Gaussians (gv.q_big, length gv.aux[0]).  A warp walking one of them alone is a serial
+// chain of trips -- a Gaussian that has grown over a 1080p frame is 8160 tiles = 64 trips, each an atomic round trip
+// in emit mode -- and was the tail of both k_preprocess and k_scatter once training had inflated a few splats.  Here
+// every CTA computes the exclusive prefix of the trip counts of the queue (redundantly, in shared memory; the queue is
+// short) and the grid's warps take work items w = gw, gw + GW, ...: item -> (entry, trip) by binary search in the
+// prefix.  EMIT = false: count per tile (RED) and per Gaussian (gv.tiles);  EMIT = true: reserve + write the keys.
+// Both passes evaluate the tile test on the STORED record, so they see bit-identical inputs.
+constexpr int kBigT = 256;
+constexpr int kBigBatch = 4096;                 // queue entries per prefix batch
+constexpr int kBigPer = kBigBatch / kBigT;      // entries per thread
+template <bool EMIT>
+__global__ void __launch_bounds__(kBigT)
+k_big_rects(int P, GeomView gv, unsigned long long* pairs, int W, int H, int gx, int exact_cull, uint32_t cap) {
+  __shared__ uint32_t s_pref[kBigBatch + 1];
+  __shared__ uint32_t s_warp[kBigT / 32];
+  const uint32_t n_all = min(gv.aux[0], (uint32_t)P);
+  if (n_all == 0u) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t gw = blockIdx.x * (kBigT / 32) + warp, GW = gridDim.x * (kBigT / 32);
+  const TileSink sink{gv.tcount, gv.tstart, gv.tcursor, EMIT ? pairs : nullptr, cap};
+  const bool cull = exact_cull != 0;
+  for (uint32_t b0 = 0; b0 < n_all; b0 += kBigBatch) {
+    const uint32_t nb = min((uint32_t)kBigBatch, n_all - b0);
+    uint32_t cnt[kBigPer], sum = 0u;
+#pragma unroll
+    for (int u = 0; u < kBigPer; ++u) {
+      const uint32_t e = (uint32_t)tid * kBigPer + u;
+      uint32_t c = 0u;
+      if (e < nb) {
+        const float4 r3 = gv.brec[gv.q_big[b0 + e]];
+        const uint32_t rcx = __float_as_uint(r3.y), rcy = __float_as_uint(r3.z);
+        const uint32_t area = ((rcx >> 16) - (rcx & 0xFFFF)) * ((rcy >> 16) - (rcy & 0xFFFF));
+        c = (area + kTripTiles - 1) / kTripTiles;
+      }
+      cnt[u] = c;
+      sum += c;
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t base = inc - sum;
+    for (int k = 0; k < warp; ++k) base += s_warp[k];
+    uint32_t total = 0u;
+    for (int k = 0; k < kBigT / 32; ++k) total += s_warp[k];
+#pragma unroll
+    for (int u = 0; u < kBigPer; ++u) {
+      const uint32_t e = (uint32_t)tid * kBigPer + u;
+      if (e < nb) s_pref[e] = base;
+      base += cnt[u];
+    }
+    if (tid == 0) s_pref[nb] = total;
+    __syncthreads();
+    for (uint32_t w = gw; w < total; w += GW) {
+      uint32_t lo = 0u, hi = nb;                         // largest e with s_pref[e] <= w (trip counts are >= 1)
+      while (hi - lo > 1u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_pref[mid] <= w) lo = mid; else hi = mid;
+      }
+      const uint32_t trip = w - s_pref[lo];
+      const uint32_t id = gv.q_big[b0 + lo];
+      const float4 r3 = gv.brec[id], e0 = gv.rec[3 * (size_t)id], e1 = gv.rec[3 * (size_t)id + 1];
+      const uint32_t rcx = __float_as_uint(r3.y), rcy = __float_as_uint(r3.z);
+      SplatRect b;
+      b.rx0 = rcx & 0xFFFF; b.rx1 = rcx >> 16; b.ry0 = rcy & 0xFFFF; b.ry1 = rcy >> 16;
+      b.x = e0.x; b.y = e0.y; b.A = -e0.z; b.B = -0.5f * e0.w; b.C = -e1.x; b.qthr = e1.z;
+      const unsigned long long key = ((unsigned long long)__float_as_uint(r3.x) << 32) | (unsigned long long)id;
+      const int wd = b.rx1 - b.rx0, n = wd * (b.ry1 - b.ry0);
+      const uint32_t kept = visit_trip(b, (int)(trip * kTripTiles), n, wd, W, H, gx, cull, sink, key);
+      if (!EMIT && lane == 0 && kept) atomicAdd(gv.tiles + id, kept);
+    }
+    __syncthreads();                                     // s_pref is rebuilt for the next batch
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -332,6 +418,17 @@ int gsb_launch_tile_scan(const GeomView& gv, int ntiles, cudaStream_t st) {
   return GSB_OK;
 }
 
+// pairs == nullptr: count mode (after k_preprocess, before the tile scan); else emit mode (beside k_scatter)
+int gsb_launch_big_rects(int P, const GeomView& gv, unsigned long long* pairs, int W, int H, int exact_cull, uint32_t cap,
+                         cudaStream_t st) {
+  const int gx = (W + kBlock - 1) / kBlock;
+  constexpr int kGrid = 148 * 2;
+  if (pairs) k_big_rects<true><<<kGrid, kBigT, 0, st>>>(P, gv, pairs, W, H, gx, exact_cull, cap);
+  else k_big_rects<false><<<kGrid, kBigT, 0, st>>>(P, gv, nullptr, W, H, gx, exact_cull, cap);
+  GSB_CUDA(cudaGetLastError());
+  return GSB_OK;
+}
+
 int gsb_launch_binning(int P, const GeomView& gv, const BinView& bv, int W, int H, int exact_cull, uint32_t cap,
                        cudaStream_t st) {
   static bool attr_set[64] = {};
@@ -346,8 +443,10 @@ int gsb_launch_binning(int P, const GeomView& gv, const BinView& bv, int W, int 
   // preprocess result, e.g. with a larger buffer after an overflow
   GSB_CUDA(cudaMemsetAsync(gv.tcursor, 0, (size_t)gx * gy * 4, st));
   if (P > 0) {
-    ProfScope ps(GSB_K_DUPLICATE, st);
+    ProfScope ps(GSB_K_DUPLICATE, st, 2);
     k_scatter<<<(P + kThreads - 1) / kThreads, kThreads, 0, st>>>(P, gv, bv, W, H, gx, exact_cull, cap);
+    const int rc = gsb_launch_big_rects(P, gv, bv.pairs, W, H, exact_cull, cap, st);                // emit mode
+    if (rc) return rc;
   }
   {
     ProfScope ps(GSB_K_SORT_TILE, st, 2);

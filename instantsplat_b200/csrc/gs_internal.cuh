@@ -71,11 +71,13 @@ struct GeomView {
   float* pose_part;    // [nblocks*16]
   float* pose_acc;     // [16]
   uint32_t* status;    // [kStWords]
-  uint32_t* tcount;    // [kMaxTiles] instances per tile (counted by k_preprocess)
+  uint32_t* aux;       // [64] per-forward counters, zeroed together with tcount (they are adjacent): [0] = length of q_big
+  uint32_t* tcount;    // [kMaxTiles] instances per tile (counted by k_preprocess / k_big_rects)
   uint32_t* tstart;    // [kMaxTiles] exclusive scan of tcount
   uint32_t* tcursor;   // [kMaxTiles] emission cursors (k_scatter)
   uint32_t* q_large;   // [kMaxTiles] tiles whose list has kSmallList < n <= kLargeList entries
   uint32_t* q_huge;    // [kMaxTiles] tiles with longer lists
+  uint32_t* q_big;     // [P] Gaussians whose tile rect exceeds kBigRect tiles (walked by k_big_rects, flattened)
   size_t total;
 };
 
@@ -95,11 +97,13 @@ static inline GeomView geom_view(void* base, int P) {
   v.pose_part = (float*)take(nb * 16 * 4);
   v.pose_acc = (float*)take(16 * 4);
   v.status = (uint32_t*)take(kStWords * 4);
+  v.aux = (uint32_t*)take(64 * 4);                        // exactly 256 bytes: tcount follows immediately
   v.tcount = (uint32_t*)take((size_t)kMaxTiles * 4);
   v.tstart = (uint32_t*)take((size_t)kMaxTiles * 4);
   v.tcursor = (uint32_t*)take((size_t)kMaxTiles * 4);
   v.q_large = (uint32_t*)take((size_t)kMaxTiles * 4);
   v.q_huge = (uint32_t*)take((size_t)kMaxTiles * 4);
+  v.q_big = (uint32_t*)take(Pp * 4);
   v.total = off;
   return v;
 }
@@ -146,6 +150,8 @@ static inline ImgView img_view(void* base, int W, int H) {
 // ---- launchers implemented in gs_bin.cu / gs_blend.cu -----------------------------------------
 // tile scan: tstart = exclusive scan(tcount), status = {R, 0, max list, 0, long-list queue lengths, serial}
 int gsb_launch_tile_scan(const gsb::GeomView& gv, int ntiles, cudaStream_t st);
+int gsb_launch_big_rects(int P, const gsb::GeomView& gv, unsigned long long* pairs, int W, int H, int exact_cull,
+                         uint32_t cap, cudaStream_t st);
 // scatter + per-tile (depth, id) sort + slab gather + ranges; cap = instance capacity of the binning buffer
 int gsb_launch_binning(int P, const gsb::GeomView& gv, const gsb::BinView& bv, int W, int H, int exact_cull,
                        uint32_t cap, cudaStream_t st);

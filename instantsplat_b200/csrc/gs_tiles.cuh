@@ -15,6 +15,9 @@
 namespace gsb {
 
 constexpr int kCoopTiles = 24;   // rects larger than this are walked by the whole warp
+constexpr int kTripTiles = 128;  // tiles per cooperative trip (4 per lane)
+constexpr int kBigRect = 128;    // rects larger than this leave the per-Gaussian kernels altogether: k_preprocess queues them
+                                 // and k_big_rects walks them as (Gaussian, trip) work items spread over the whole grid
 
 struct TileSink {
   // count mode: tcount != nullptr, pairs == nullptr
@@ -112,9 +115,51 @@ __device__ __forceinline__ void warp_sink_masks(uint32_t mask, int rx0, int ry0,
   }
 }
 
+// One cooperative trip: tiles [base, base + kTripTiles) of the rect (row-major index i -> (ry0 + i / w, rx0 + i % w)),
+// four per lane, every atomic issued before the first result is consumed.  All 32 lanes call with the same arguments;
+// returns the number of kept tiles of the trip.
+__device__ __forceinline__ uint32_t visit_trip(const SplatRect& b, int base, int n, int w, int W, int H, int gx, bool cull,
+                                               const TileSink& s, unsigned long long bkey) {
+  const int lane = threadIdx.x & 31;
+  constexpr int kU = kTripTiles / 32;
+  bool keep[kU];
+  uint32_t tile[kU], pos[kU];
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    const int i = base + u * 32 + lane;
+    keep[u] = false;
+    tile[u] = 0u;
+    if (i < n) {
+      const int ty = b.ry0 + i / w, tx = b.rx0 + i - (i / w) * w;
+      keep[u] = tile_kept(b, tx, ty, W, H, cull);
+      tile[u] = (uint32_t)(ty * gx + tx);
+    }
+  }
+  if (s.pairs) {
+#pragma unroll
+    for (int u = 0; u < kU; ++u) pos[u] = keep[u] ? atomicAdd(s.tcursor + tile[u], 1u) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (keep[u] && pos[u] < s.tcount[tile[u]]) {
+        const uint32_t dst = s.tstart[tile[u]] + pos[u];
+        if (dst < s.cap) s.pairs[dst] = bkey;
+      }
+  } else {
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (keep[u]) atomicAdd(s.tcount + tile[u], 1u);
+  }
+  uint32_t run = 0;
+#pragma unroll
+  for (int u = 0; u < kU; ++u) run += __popc(__ballot_sync(0xffffffffu, keep[u]));
+  return run;
+}
+
 // Gaussians whose rect spans more than kCoopTiles tiles are walked by the WHOLE WARP (one tile per lane per
 // step) instead of one thread looping over up to thousands of tiles -- the per-thread loop is a performance
-// cliff once a few Gaussians grow large.  Must be called by all 32 lanes; `mine` says whether this lane's
+// cliff once a few Gaussians grow large.  (Rects beyond kBigRect do not come here: a Gaussian that has grown over the
+// whole frame is thousands of tiles = a serial chain of trips for ONE warp and the tail of the whole kernel; those are
+// queued and flattened over the grid by k_big_rects.)  Must be called by all 32 lanes; `mine` says whether this lane's
 // Gaussian wants the cooperative path.  Returns the lane's kept-tile count.
 __device__ __forceinline__ uint32_t visit_tiles_coop(bool mine, const SplatRect& p, int W, int H, int gx, bool cull,
                                                      const TileSink& s, unsigned long long key) {
@@ -133,41 +178,7 @@ __device__ __forceinline__ uint32_t visit_tiles_coop(bool mine, const SplatRect&
     const unsigned long long bkey = __shfl_sync(0xffffffffu, key, src);
     const int w = b.rx1 - b.rx0, n = w * (b.ry1 - b.ry0);
     uint32_t run = 0;
-    // kU x 32 tiles per trip, and within a trip every atomic is issued before the first result is consumed: a
-    // Gaussian that has grown over the whole frame (thousands of tiles) is a serial chain of trips for ONE warp, so the
-    // length of a trip -- one atomic round trip instead of kU -- is the tail of the whole kernel
-    constexpr int kU = 4;
-    for (int base = 0; base < n; base += 32 * kU) {
-      bool keep[kU];
-      uint32_t tile[kU], pos[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int i = base + u * 32 + lane;
-        keep[u] = false;
-        tile[u] = 0u;
-        if (i < n) {
-          const int ty = b.ry0 + i / w, tx = b.rx0 + i - (i / w) * w;
-          keep[u] = tile_kept(b, tx, ty, W, H, cull);
-          tile[u] = (uint32_t)(ty * gx + tx);
-        }
-      }
-      if (s.pairs) {
-#pragma unroll
-        for (int u = 0; u < kU; ++u) pos[u] = keep[u] ? atomicAdd(s.tcursor + tile[u], 1u) : 0xFFFFFFFFu;
-#pragma unroll
-        for (int u = 0; u < kU; ++u)
-          if (keep[u] && pos[u] < s.tcount[tile[u]]) {
-            const uint32_t dst = s.tstart[tile[u]] + pos[u];
-            if (dst < s.cap) s.pairs[dst] = bkey;
-          }
-      } else {
-#pragma unroll
-        for (int u = 0; u < kU; ++u)
-          if (keep[u]) atomicAdd(s.tcount + tile[u], 1u);
-      }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) run += __popc(__ballot_sync(0xffffffffu, keep[u]));
-    }
+    for (int base = 0; base < n; base += kTripTiles) run += visit_trip(b, base, n, w, W, H, gx, cull, s, bkey);
     if (lane == src) result = run;
   }
   return result;

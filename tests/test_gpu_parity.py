@@ -200,6 +200,44 @@ def test_exact_cull_is_lossless():
         assert rel_err(a_g[k], b_g[k]) < 1e-4, k
 
 
+def test_big_rects_flattened_path_vs_oracle():
+    """Gaussians whose tile rect exceeds 128 tiles are not walked by their own warp: k_preprocess queues them and
+    k_big_rects counts / emits them as (Gaussian, trip) work items spread over the grid (gs_bin.cu).  40 Gaussians
+    blown up 12x (a few hundred tiles each) and 3 blown up 150x (the whole 640x400 frame = 1000 tiles) on a 20k scene:
+    image and gradients vs the oracle on a tile subset that includes tiles under the big ones, the instance count is
+    reproducible, and the lossless cull stays lossless on this path."""
+    import instantsplat_b200.rasterizer as R
+    sc = surface_scene(20_000, 3, 640, 400, seed=23, sh_degree=3)
+    mid = enlarge_some(sc, 40, 12.0, seed=6)
+    huge = enlarge_some(sc, 3, 150.0, seed=7)
+    sc.params["opacity"][huge] = -2.0                 # keep the frame-filling ones translucent: everything behind still counts
+    with torch.no_grad():
+        cam = O.Camera.instantsplat(sc.width, sc.height, sc.fovx, sc.fovy, sh_degree=3)
+        idx = torch.cat([mid, huge])
+        means, rots = O.pose_pretransform(sc.params["xyz"][idx], sc.params["rotation"][idx], sc.poses[1])
+        shs = torch.cat([sc.params["f_dc"][idx], sc.params["f_rest"][idx]], dim=1)
+        pr = O.project(means, torch.exp(sc.params["scaling"][idx]), rots, torch.sigmoid(sc.params["opacity"][idx]), shs, cam)
+    assert int((pr["ntiles"] > 128).sum()) >= 10 and int(pr["ntiles"].max()) >= 900, pr["ntiles"]
+    extra = tiles_under(sc, 1, 3, idx)[:8]
+    compare_fused("big rects (flattened count/emit), 20k 640x400 view 1", sc, 1, 3, torch.tensor([0.1, 0.2, 0.3]),
+                  tiles=stratified_tiles(40, 25, 10, 41, extra))
+    sc.poses = sc.poses[1:2]
+    bg = torch.zeros(3)
+    gt = torch.rand(3, sc.height, sc.width, generator=torch.Generator().manual_seed(4))
+    try:
+        R.EXACT_CULL = True
+        a_img, a_r, _, a_g = cuda_run(sc, 3, bg, gt)
+        a2_img = cuda_run(sc, 3, bg, gt)[0]
+        R.EXACT_CULL = False
+        b_img, b_r, _, b_g = cuda_run(sc, 3, bg, gt)
+    finally:
+        R.EXACT_CULL = True
+    assert torch.equal(a_img, a2_img)                 # deterministic although the emission order is not
+    assert torch.equal(a_r, b_r) and float((a_img - b_img).abs().max()) <= 1e-6
+    for k in NAMES + ("pose",):
+        assert rel_err(a_g[k], b_g[k]) < 1e-4, k
+
+
 def test_sync_free_capacity_overflow_is_repaired():
     """The autograd boundary sizes the binning buffer from earlier counts and launches the render phase without waiting
     for the instance count.  With a (forced) far too small estimate the tile lists are truncated; the check at the end of

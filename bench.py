@@ -43,9 +43,6 @@ def parse():
     ap.add_argument("--blend-version", type=int, default=0, help="debug: force blend kernel version 1|2|3")
     ap.add_argument("--graph", action="store_true",
                     help="multi-GPU with --exchange fused_p2p: replay each rank's iteration (exchange included) from CUDA graphs")
-    ap.add_argument("--no-overlap", action="store_true",
-                    help="single GPU: keep the SH colour pass and the SH tensors' Adam update on the main stream "
-                         "(default: they run on a second stream beside the next iteration's geometry / binning)")
     ap.add_argument("--no-graph", action="store_true",
                     help="do not replay the iteration from CUDA graphs (single GPU, and multi-GPU with --exchange fused_p2p)")
     ap.add_argument("--exchange", default="fused_p2p", choices=["allreduce", "fused_p2p", "fused_p2p_nccl"],
@@ -306,9 +303,8 @@ def run_b200(args):
     # ms/step, profiles/r02_bench_n2_graph*.json): the host already runs ahead of a step that waits on its peers, so
     # eager stays the default there and --graph opts in
     use_graph = (world == 1 and not args.no_graph) or (world > 1 and args.graph and args.exchange == "fused_p2p")
-    overlap = use_graph and world == 1 and not args.no_overlap
     tr = I.JointTrainer(sc, dev, gt_images=gt_dev, world_size=world, rank=rank, exchange=args.exchange,
-                        use_graph=use_graph, overlap=overlap)
+                        use_graph=use_graph)
     # ---- e2e pipeline through the public API: this step's GT image is copied H2D from pinned memory on a copy
     # stream (double buffered, so the copy of step s+1 overlaps the compute of step s) and every step's loss is
     # read back to the host (asynchronously, consumed one step later).
@@ -361,7 +357,6 @@ def run_b200(args):
         e0.record()
         for s in range(n):
             fn(first + s)
-        tr.join()                        # overlap mode: the last step's side-stream work belongs to the timed region
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -593,8 +588,6 @@ def run_b200(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.config, sc), "views_per_step": world,
                    "parallelism": f"view-sharded dp{world}", "exchange": tr.exchange if world > 1 else "none", "P": sc.P, "R_mean": tr.last_R,
-                   "overlap": ("SH colour pass + SH Adam on a second stream beside the next iteration's geometry/binning"
-                               if overlap else "none"),
                    "launch_mode": ("CUDA-graph replay of the whole iteration (one graph per view); per-kernel table from "
                                    f"a second, eagerly launched timed region of {Kp} steps at {ms_prof / Kp:.3f} ms/step")
                    if use_graph else "eager launches",

@@ -121,23 +121,6 @@ GSB_API int gsb_preprocess(const GsbCamera* cam, const GsbGaussians* g, void* ge
 GSB_API int gsb_render(const GsbCamera* cam, int32_t P, void* geom, void* binning, size_t binning_bytes,
                int64_t R, void* image, float* out_color, uint32_t* status_host, gsb_stream_t stream);
 
-/* The same forward in finer steps, for callers that overlap the colour pass with the binning (JointTrainer's overlap
- * mode runs SH Adam + colour on a second stream while geometry, tile scan, scatter and tile sort run on the first):
- *   gsb_preprocess_geom   = gsb_preprocess without SH->RGB (no SH tensor is read; not for colors_precomp inputs)
- *   gsb_preprocess_color  = SH->RGB of every Gaussian into the same geom buffer (record row 2, clamp flags); depends
- *                           on nothing gsb_preprocess_geom writes, so it may run before, after or beside it
- *   gsb_binning           = first half of gsb_render (scatter + per-tile sort)
- *   gsb_blend_forward     = second half of gsb_render (needs geom pass, colour pass and binning complete)
- * gsb_preprocess_geom + gsb_preprocess_color + gsb_binning + gsb_blend_forward == gsb_preprocess + gsb_render. */
-GSB_API int gsb_preprocess_geom(const GsbCamera* cam, const GsbGaussians* g, void* geom, size_t geom_bytes,
-                                int32_t* radii, uint32_t* status_host, gsb_stream_t stream);
-GSB_API int gsb_preprocess_color(const GsbCamera* cam, const GsbGaussians* g, void* geom, size_t geom_bytes,
-                                 gsb_stream_t stream);
-GSB_API int gsb_binning(const GsbCamera* cam, int32_t P, void* geom, void* binning, size_t binning_bytes, int64_t R,
-                        gsb_stream_t stream);
-GSB_API int gsb_blend_forward(const GsbCamera* cam, int32_t P, void* geom, void* binning, size_t binning_bytes,
-                              int64_t R, void* image, float* out_color, uint32_t* status_host, gsb_stream_t stream);
-
 /* Device address of the 8 status words inside `geom` ([0] R, [1] overflow, [2] longest list, [3] slow-path
  * tiles): lets device code (e.g. gsb_adam_step's skip flag) react to an overflow without a host round trip. */
 GSB_API uint32_t* gsb_status_device(void* geom, int32_t P);
@@ -238,12 +221,6 @@ GSB_API int gsb_peer_exchange(int32_t world, int32_t rank, void* const* peer_sig
  * host refreshes the array (learning-rate schedule, bias correction) before every replay. */
 GSB_API int gsb_adam_step_ex(int32_t n, const GsbAdamTensor* tensors_host, uint32_t* flags,
                              const uint32_t* skip_if_nonzero, const float* step_sizes_dev, gsb_stream_t stream);
-
-/* gsb_adam_step_ex from a persistent grid of at most max_ctas CTAs (256 threads each): the update is HBM-bound and needs
- * bytes in flight, not occupancy, so a small grid leaves most of every SM to kernels of another stream. */
-GSB_API int gsb_adam_step_bg(int32_t n, const GsbAdamTensor* tensors_host, uint32_t* flags,
-                             const uint32_t* skip_if_nonzero, const float* step_sizes_dev, int32_t max_ctas,
-                             gsb_stream_t stream);
 
 typedef struct GsbShardPiece { /* (one tensor's segment) intersected with (this rank's shard) */
   int64_t begin, end;          /* flat-buffer element range, multiples of 4 */

@@ -63,8 +63,7 @@ EXPORTS = ("gsb_geom_bytes", "gsb_binning_bytes", "gsb_image_bytes", "gsb_prepro
            "gsb_loss_forward", "gsb_loss_backward", "gsb_adam_step", "gsb_last_error",
            "gsb_abi_version", "gsb_profile_enable", "gsb_profile_collect", "gsb_launch_count", "gsb_set_option", "gsb_adam_gate",
            "gsb_ipc_alloc", "gsb_ipc_open", "gsb_ipc_close", "gsb_ipc_free", "gsb_fused_rs_adam_ag",
-           "gsb_knn_scratch_bytes", "gsb_knn_mean_dist2", "gsb_status_device", "gsb_adam_step_gated", "gsb_blend_stats", "gsb_l1_mask_fwd_bwd", "gsb_track_step", "gsb_peer_signal_bytes", "gsb_peer_barrier", "gsb_peer_exchange", "gsb_adam_step_ex",
-           "gsb_preprocess_geom", "gsb_preprocess_color", "gsb_binning", "gsb_blend_forward", "gsb_adam_step_bg")
+           "gsb_knn_scratch_bytes", "gsb_knn_mean_dist2", "gsb_status_device", "gsb_adam_step_gated", "gsb_blend_stats", "gsb_l1_mask_fwd_bwd", "gsb_track_step", "gsb_peer_signal_bytes", "gsb_peer_barrier", "gsb_peer_exchange", "gsb_adam_step_ex")
 KERNEL_IDS = ("preprocess", "sort_depth", "scan", "duplicate", "sort_tile", "gather", "blend_fwd", "blend_bwd",
               "preprocess_bwd", "loss_fwd", "loss_bwd", "adam")
 
@@ -102,13 +101,6 @@ def lib() -> ctypes.CDLL:
     L.gsb_image_bytes.argtypes = [i32, i32]
     L.gsb_preprocess.argtypes = [ctypes.POINTER(GsbCamera), ctypes.POINTER(GsbGaussians), vp, sz, vp, vp, vp]
     L.gsb_render.argtypes = [ctypes.POINTER(GsbCamera), i32, vp, vp, sz, i64, vp, vp, vp, vp]
-    L.gsb_preprocess_geom.argtypes = L.gsb_preprocess.argtypes
-    L.gsb_preprocess_color.argtypes = [ctypes.POINTER(GsbCamera), ctypes.POINTER(GsbGaussians), vp, sz, vp]
-    L.gsb_binning.argtypes = [ctypes.POINTER(GsbCamera), i32, vp, vp, sz, i64, vp]
-    L.gsb_blend_forward.argtypes = L.gsb_render.argtypes
-    L.gsb_adam_step_bg.argtypes = [i32, ctypes.POINTER(GsbAdamTensor), vp, vp, vp, i32, vp]
-    for f in ("gsb_preprocess_geom", "gsb_preprocess_color", "gsb_binning", "gsb_blend_forward", "gsb_adam_step_bg"):
-        getattr(L, f).restype = ctypes.c_int
     L.gsb_blend_stats.argtypes = [ctypes.POINTER(GsbCamera), i32, vp, vp, i64, vp, vp, vp, vp, vp]
     L.gsb_blend_stats.restype = ctypes.c_int
     fl = ctypes.c_float

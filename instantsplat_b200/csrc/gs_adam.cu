@@ -89,32 +89,16 @@ __device__ __forceinline__ void adam_elem(const AdamT& t, float step, bool gate,
   p = __fadd_rn(p, __fmul_rn(-(step * lr_mul), upd));
 }
 
-// vblock = the virtual block (2048 consecutive elements of one tensor) this CTA iteration works on
-__device__ __forceinline__ void adam_block(const AdamArgs& a, const unsigned int* __restrict__ flags, unsigned int vblock);
-
 __global__ void __launch_bounds__(kAT) k_adam(AdamArgs a, const unsigned int* __restrict__ flags,
                                               const unsigned int* __restrict__ skip) {
   if (skip && *skip) return;     // e.g. the forward's overflow word: the caller redoes the step with larger buffers
-  adam_block(a, flags, blockIdx.x);
-}
-
-// Same update from a SMALL persistent grid (grid-stride over the virtual blocks): the kernel then occupies only a
-// fraction of every SM's thread slots and can share the GPU with latency-bound kernels of another stream -- it is
-// HBM-bound and needs bytes in flight, not occupancy (JointTrainer overlap mode: SH tensors on the side stream).
-__global__ void __launch_bounds__(kAT) k_adam_bg(AdamArgs a, const unsigned int* __restrict__ flags,
-                                                 const unsigned int* __restrict__ skip, unsigned int nblocks) {
-  if (skip && *skip) return;
-  for (unsigned int vb = blockIdx.x; vb < nblocks; vb += gridDim.x) adam_block(a, flags, vb);
-}
-
-__device__ __forceinline__ void adam_block(const AdamArgs& a, const unsigned int* __restrict__ flags, unsigned int vblock) {
-  const int k = find_tensor(a, vblock);
+  const int k = find_tensor(a, blockIdx.x);
   const AdamT& t = a.t[k];
   const bool gate = flags[k] != 0;
   // step size = lr * sqrt(1-b2^t)/(1-b1^t): a launch argument, or (CUDA-graph replay: arguments are frozen) read from
   // a device array the host refreshes before every replay
   const float step = a.step_dev ? a.step_dev[k] : t.step;
-  const long long base = (long long)(vblock - t.first_block) * kPerBlock;
+  const long long base = (long long)(blockIdx.x - t.first_block) * kPerBlock;
   const bool vec = ((((uintptr_t)t.p | (uintptr_t)t.g | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0);
   if (vec && base + kPerBlock <= t.numel) {
 #pragma unroll
@@ -229,33 +213,6 @@ extern "C" GSB_API int gsb_adam_step_ex(int32_t n, const GsbAdamTensor* ts, uint
     e = cudaGetLastError();
   }
   return finish(e, "gsb_adam_step");
-}
-
-// max_ctas > 0: the update runs from a persistent grid of at most max_ctas CTAs (see k_adam_bg)
-extern "C" GSB_API int gsb_adam_step_bg(int32_t n, const GsbAdamTensor* ts, uint32_t* flags,
-                                        const uint32_t* skip_if_nonzero, const float* step_sizes_dev, int32_t max_ctas,
-                                        gsb_stream_t stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
-  if (n < 0 || n > GSB_ADAM_MAX_TENSORS || (n > 0 && (!ts || !flags)) || max_ctas <= 0) {
-    gsb_set_error("gsb_adam_step_bg: bad argument");
-    return GSB_ERR_INVALID;
-  }
-  if (n == 0) return GSB_OK;
-  AdamArgs a;
-  unsigned int nb;
-  int rc = build_args(n, ts, a, nb);
-  if (rc) return rc;
-  a.step_dev = step_sizes_dev;
-  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, st);
-  if (e == cudaSuccess && nb > 0) {
-    gsb_count_launch(2);
-    int slot = gsb_prof_begin(GSB_K_ADAM, st);
-    k_adam_gate<<<n * kGateSlots, kAT, 0, st>>>(a, flags);
-    k_adam_bg<<<nb < (unsigned int)max_ctas ? nb : (unsigned int)max_ctas, kAT, 0, st>>>(a, flags, skip_if_nonzero, nb);
-    gsb_prof_end(slot, st);
-    e = cudaGetLastError();
-  }
-  return finish(e, "gsb_adam_step_bg");
 }
 
 extern "C" GSB_API int gsb_adam_step_gated(int32_t n, const GsbAdamTensor* ts, uint32_t* flags,

@@ -196,7 +196,7 @@ GS_HD void sh_to_rgb_bwd(int D, const float* sh_rest, float x, float y, float z,
 }
 
 // The mean handed to the rasterizer: the fused InstantSplat pose pre-transform R m + t (or m itself).  Explicit fma
-// chain: the geometry kernel and the separate colour kernel (k_color) must obtain the same bits.
+// chain, so that every kernel that needs the transformed mean obtains the same bits.
 GS_HD void pose_mean(const CamConst& c, const float* m, float* mc) {
   if (c.pose_on) {
     mc[0] = fmaf(c.Rc[0], m[0], fmaf(c.Rc[1], m[1], fmaf(c.Rc[2], m[2], c.tc[0])));

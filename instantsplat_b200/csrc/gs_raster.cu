@@ -116,7 +116,6 @@ struct InPtrs {
   int sh_packed;
   int vec_ok;       // all base pointers 16-byte aligned
   int exact_cull;
-  int skip_color;   // geometry only: SH->RGB (record row 2, clamp flags) is produced by k_color, possibly concurrently
 };
 
 // ------------------------------------------------------------------------------------------
@@ -343,7 +342,7 @@ k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
   }
   int first = blockIdx.x * kPT;
   int nv = min(kPT, in.P - first);
-  bool use_sh = in.colors == nullptr && !in.skip_color;
+  bool use_sh = in.colors == nullptr;
   __syncthreads();
   load_block_inputs(in, first, nv, use_sh, cam->D, cam->M, sm);
   __syncthreads();
@@ -367,10 +366,8 @@ k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
     if (use_sh) {
       const ShRows sr = sh_rows(in.sh_packed, cam->M);
       project_color(*cam, sm + kSmSh + sr.dc_stride * t, sm + kSmSh + sr.rest_off + sr.rest_stride * t, p);
-    } else if (!in.skip_color) {
-      p.rgb[0] = in.colors[3 * i]; p.rgb[1] = in.colors[3 * i + 1]; p.rgb[2] = in.colors[3 * i + 2];
     } else {
-      p.rgb[0] = p.rgb[1] = p.rgb[2] = 0.f;
+      p.rgb[0] = in.colors[3 * i]; p.rgb[1] = in.colors[3 * i + 1]; p.rgb[2] = in.colors[3 * i + 2];
     }
     qthr = cull_threshold(p.opacity);
     // The tile coverage is decided on the record exactly as it is stored (conic and threshold in the log2 domain), so
@@ -429,68 +426,12 @@ k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
                              __uint_as_float((uint32_t)p.ry0 | ((uint32_t)p.ry1 << 16)), __uint_as_float(kmask));
     gv.tiles[i] = ntiles;
     if (big) gv.q_big[atomicAdd(gv.aux, 1u)] = (uint32_t)i;     // at most once per Gaussian: the queue holds P entries
-    if (!in.skip_color) gv.clamped[i] = (uint8_t)p.clamped;
+    gv.clamped[i] = (uint8_t)p.clamped;
     radii[i] = p.radius;
   }
   __syncthreads();
   float4* dst4 = gv.rec + 3 * (size_t)first;
-  if (!in.skip_color) {
-    for (int k = threadIdx.x; k < 3 * nv; k += kPT) dst4[k] = sm4[k];
-  } else {                                           // rows 0 and 1 only: row 2 belongs to k_color
-    for (int k = threadIdx.x; k < 2 * nv; k += kPT) { const int q = k + (k >> 1); dst4[q] = sm4[q]; }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_color: SH -> RGB for every Gaussian (record row 2 and the clamp flags), as a kernel of its own
-// ------------------------------------------------------------------------------------------
-// The colours are the only part of the projection that needs the SH tensors (81 % of the parameter bytes), and the
-// only consumer of the colours is the blend.  Split off, the colour pass -- and the Adam update of the SH tensors that
-// precedes it -- can run on a second stream while the geometry pass, the tile scan, the scatter and the tile sort run
-// on the first (JointTrainer, overlap mode).  It depends on nothing the geometry pass produces: the camera constants
-// are rebuilt per CTA from the same inputs, and colours are computed for every Gaussian (no visibility test that could
-// disagree with the geometry pass in the last bit).
-constexpr int kColSh = 3 * kPT;                                  // smem: xyz[3N] | sh dc[3N] rest[45N] (or packed rows)
-constexpr size_t kColorSmem = sizeof(CamConst) + 16 + (size_t)(3 * kPT + kRowPad * kPT) * 4;
-__global__ void __launch_bounds__(kPT)
-k_color(InPtrs in, CamArgs ca, GeomView gv) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  CamConst* cam = reinterpret_cast<CamConst*>(smem_raw);
-  float* sm = reinterpret_cast<float*>(smem_raw + ((sizeof(CamConst) + 15) / 16) * 16);
-  if (threadIdx.x == 0) fill_cam(*cam, ca);
-  const int first = blockIdx.x * kPT;
-  const int nv = min(kPT, in.P - first);
-  const bool vec = in.vec_ok != 0;
-  const int M = ca.M, D = ca.D;
-  if (vec && nv == kPT && !in.sh_packed && M == 16) {
-    constexpr int N3 = 3 * kPT / 4, NR = 45 * kPT / 4;
-    float4 rx[1], rd[1], rr[(NR + kPT - 1) / kPT];
-    ld_batch<N3, 1>(rx, in.means + (size_t)3 * first);
-    ld_batch<N3, 1>(rd, in.sh_dc + (size_t)3 * first);
-    if (D > 0) ld_batch<NR, (NR + kPT - 1) / kPT>(rr, in.sh_rest + (size_t)45 * first);
-    st_batch<N3, 1>(rx, sm);
-    st_batch<N3, 1>(rd, sm + kColSh);
-    if (D > 0) st_batch<NR, (NR + kPT - 1) / kPT>(rr, sm + kColSh + 3 * kPT);
-  } else {
-    copy_in(sm, in.means + (size_t)3 * first, 3 * nv, vec);
-    if (in.sh_packed) {
-      stage_in(sm + kColSh, in.sh_dc + (size_t)3 * M * first, 3 * M * nv, 3 * M, kRowPad, 0, vec);
-    } else {
-      copy_in(sm + kColSh, in.sh_dc + (size_t)3 * first, 3 * nv, vec);
-      if (D > 0 && M > 1) copy_in(sm + kColSh + 3 * kPT, in.sh_rest + (size_t)3 * (M - 1) * first, 3 * (M - 1) * nv, vec);
-    }
-  }
-  __syncthreads();
-  const int t = threadIdx.x;
-  if (t >= nv) return;
-  const int i = first + t;
-  Proj p;
-  const float m[3] = {sm[3 * t], sm[3 * t + 1], sm[3 * t + 2]};
-  pose_mean(*cam, m, p.mc);
-  const ShRows sr = sh_rows(in.sh_packed, M);
-  project_color(*cam, sm + kColSh + sr.dc_stride * t, sm + kColSh + sr.rest_off + sr.rest_stride * t, p);
-  gv.rec[3 * (size_t)i + 2] = make_float4(p.rgb[0], p.rgb[1], p.rgb[2], 0.f);
-  gv.clamped[i] = (uint8_t)p.clamped;
+  for (int k = threadIdx.x; k < 3 * nv; k += kPT) dst4[k] = sm4[k];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -687,7 +628,7 @@ static int make_inptrs(const GsbCamera* cam, const GsbGaussians* g, InPtrs& in) 
   }
   in.P = g->P; in.means = g->means3D; in.scales = g->scales; in.rots = g->rotations; in.opac = g->opacities;
   in.sh_dc = g->sh_dc; in.sh_rest = g->sh_rest; in.colors = g->colors_precomp; in.cov3D = g->cov3D_precomp;
-  in.sh_packed = g->sh_packed; in.exact_cull = cam->exact_cull; in.skip_color = 0;
+  in.sh_packed = g->sh_packed; in.exact_cull = cam->exact_cull;
   uintptr_t a = (uintptr_t)g->means3D | (uintptr_t)g->scales | (uintptr_t)g->rotations |
                 (uintptr_t)g->opacities | (uintptr_t)g->sh_dc | (uintptr_t)g->sh_rest;
   in.vec_ok = (a & 15) == 0;
@@ -717,14 +658,13 @@ static CamArgs cam_args(const GsbCamera* cam, const GsbGaussians* g) {
   return a;
 }
 
-static int preprocess_impl(const GsbCamera* cam, const GsbGaussians* g, void* geom, size_t geom_bytes, int32_t* radii,
-                           uint32_t* status_host, bool skip_color, cudaStream_t st) {
+extern "C" GSB_API int gsb_preprocess(const GsbCamera* cam, const GsbGaussians* g, void* geom, size_t geom_bytes,
+                              int32_t* radii, uint32_t* status_host, gsb_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
   InPtrs in;
   int rc = make_inptrs(cam, g, in);
   if (rc) return rc;
   GSB_REQUIRE(geom && (radii || g->P == 0), "null buffer");
-  if (skip_color) GSB_REQUIRE(in.colors == nullptr, "gsb_preprocess_geom: colors_precomp has no colour pass to split off");
-  in.skip_color = skip_color ? 1 : 0;
   const int P = g->P;
   GeomView gv = geom_view(geom, P);
   if (gv.total > geom_bytes) { gsb_set_error("geom buffer too small"); return GSB_ERR_CAPACITY; }
@@ -749,39 +689,6 @@ static int preprocess_impl(const GsbCamera* cam, const GsbGaussians* g, void* ge
   return GSB_OK;
 }
 
-extern "C" GSB_API int gsb_preprocess(const GsbCamera* cam, const GsbGaussians* g, void* geom, size_t geom_bytes,
-                              int32_t* radii, uint32_t* status_host, gsb_stream_t stream_) {
-  return preprocess_impl(cam, g, geom, geom_bytes, radii, status_host, false, (cudaStream_t)stream_);
-}
-
-// gsb_preprocess without the SH -> RGB part; gsb_preprocess_color supplies it (any stream, any order relative to the
-// geometry pass; both must have completed before gsb_blend_forward).
-extern "C" GSB_API int gsb_preprocess_geom(const GsbCamera* cam, const GsbGaussians* g, void* geom, size_t geom_bytes,
-                                           int32_t* radii, uint32_t* status_host, gsb_stream_t stream_) {
-  return preprocess_impl(cam, g, geom, geom_bytes, radii, status_host, true, (cudaStream_t)stream_);
-}
-
-extern "C" GSB_API int gsb_preprocess_color(const GsbCamera* cam, const GsbGaussians* g, void* geom, size_t geom_bytes,
-                                            gsb_stream_t stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
-  InPtrs in;
-  int rc = make_inptrs(cam, g, in);
-  if (rc) return rc;
-  GSB_REQUIRE(geom && in.colors == nullptr && in.sh_dc, "gsb_preprocess_color: needs SH inputs");
-  in.skip_color = 0;
-  const int P = g->P;
-  GeomView gv = geom_view(geom, P);
-  if (gv.total > geom_bytes) { gsb_set_error("geom buffer too small"); return GSB_ERR_CAPACITY; }
-  rc = ensure_attrs();
-  if (rc) return rc;
-  if (P > 0) {
-    ProfScope ps(GSB_K_PREPROCESS, st);
-    k_color<<<(P + kPT - 1) / kPT, kPT, kColorSmem, st>>>(in, cam_args(cam, g), gv);
-  }
-  GSB_CUDA(cudaGetLastError());
-  return GSB_OK;
-}
-
 extern "C" GSB_API int gsb_render(const GsbCamera* cam, int32_t P, void* geom, void* binning, size_t binning_bytes,
                           int64_t R, void* image, float* out_color, uint32_t* status_host, gsb_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
@@ -795,37 +702,6 @@ extern "C" GSB_API int gsb_render(const GsbCamera* cam, int32_t P, void* geom, v
   int rc = gsb_launch_binning(P, gv, bv, W, H, cam->exact_cull, (uint32_t)R, st);
   if (rc) return rc;
   rc = gsb_launch_blend_fwd(gv, bv, iv, cam->bg, W, H, out_color, st);
-  if (rc) return rc;
-  if (status_host) GSB_CUDA(cudaMemcpyAsync(status_host, gv.status, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  GSB_CUDA(cudaGetLastError());
-  return GSB_OK;
-}
-
-// The two halves of gsb_render as separate calls (the colour pass may be joined in between).
-extern "C" GSB_API int gsb_binning(const GsbCamera* cam, int32_t P, void* geom, void* binning, size_t binning_bytes,
-                                   int64_t R, gsb_stream_t stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
-  GSB_REQUIRE(cam && geom && binning, "null buffer");
-  GSB_REQUIRE(R >= 0 && R < (int64_t)0x7fffffff, "R out of range");
-  const int W = cam->width, H = cam->height;
-  GeomView gv = geom_view(geom, P);
-  BinView bv = bin_view(binning, R, W, H);
-  if (bv.total > binning_bytes) { gsb_set_error("binning buffer too small"); return GSB_ERR_CAPACITY; }
-  return gsb_launch_binning(P, gv, bv, W, H, cam->exact_cull, (uint32_t)R, st);
-}
-
-extern "C" GSB_API int gsb_blend_forward(const GsbCamera* cam, int32_t P, void* geom, void* binning, size_t binning_bytes,
-                                         int64_t R, void* image, float* out_color, uint32_t* status_host,
-                                         gsb_stream_t stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
-  GSB_REQUIRE(cam && geom && binning && image && out_color, "null buffer");
-  GSB_REQUIRE(R >= 0 && R < (int64_t)0x7fffffff, "R out of range");
-  const int W = cam->width, H = cam->height;
-  GeomView gv = geom_view(geom, P);
-  BinView bv = bin_view(binning, R, W, H);
-  if (bv.total > binning_bytes) { gsb_set_error("binning buffer too small"); return GSB_ERR_CAPACITY; }
-  ImgView iv = img_view(image, W, H);
-  int rc = gsb_launch_blend_fwd(gv, bv, iv, cam->bg, W, H, out_color, st);
   if (rc) return rc;
   if (status_host) GSB_CUDA(cudaMemcpyAsync(status_host, gv.status, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   GSB_CUDA(cudaGetLastError());

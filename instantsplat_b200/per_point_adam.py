@@ -14,22 +14,21 @@ from . import _lib
 from ._lib import ADAM_MAX_TENSORS, GsbAdamTensor, check
 
 
-def launch_adam(entries, flags, skip_ptr=None, step_sizes_dev=None, max_ctas=0):
+def launch_adam(entries, flags, skip_ptr=None, step_sizes_dev=None):
     """entries: list of dicts(param, grad, exp_avg, exp_avg_sq, per_point_lr, step_size, beta1, beta2,
     eps, weight_decay, grad_scale, row_len).  skip_ptr: optional device address of a word that, when non-zero,
     makes the device skip the whole update (gsb_adam_step_gated).  step_sizes_dev: optional fp32 device tensor with one
-    step size per entry, read by the kernel instead of the launch arguments (CUDA-graph replay).  max_ctas > 0: run the
-    update from a small persistent grid (gsb_adam_step_bg) so that it can share the GPU with another stream's kernels."""
+    step size per entry, read by the kernel instead of the launch arguments (CUDA-graph replay)."""
     if step_sizes_dev is not None and len(entries) > ADAM_MAX_TENSORS:
         raise _lib.GsbError("device-side step sizes support at most one launch (8 tensors)")
     L = _lib.lib()
     if not entries:
         return
     with torch.cuda.device(entries[0]["param"].device):       # launch on the tensors' device, whatever is current
-        _launch_adam_on_device(L, entries, flags, skip_ptr, step_sizes_dev, max_ctas)
+        _launch_adam_on_device(L, entries, flags, skip_ptr, step_sizes_dev)
 
 
-def _launch_adam_on_device(L, entries, flags, skip_ptr, step_sizes_dev, max_ctas=0):
+def _launch_adam_on_device(L, entries, flags, skip_ptr, step_sizes_dev):
     for i in range(0, len(entries), ADAM_MAX_TENSORS):
         chunk = entries[i:i + ADAM_MAX_TENSORS]
         arr = (GsbAdamTensor * len(chunk))()
@@ -42,12 +41,9 @@ def _launch_adam_on_device(L, entries, flags, skip_ptr, step_sizes_dev, max_ctas
             t.grad_scale = float(e.get("grad_scale", 1.0))
             t.step_size, t.beta1, t.beta2 = float(e["step_size"]), float(e["beta1"]), float(e["beta2"])
             t.eps, t.weight_decay = float(e["eps"]), float(e["weight_decay"])
-        sd = None if step_sizes_dev is None else step_sizes_dev.data_ptr()
-        if max_ctas > 0:
-            check(L.gsb_adam_step_bg(len(chunk), arr, flags.data_ptr(), skip_ptr, sd, int(max_ctas), _lib.stream_ptr()),
-                  "gsb_adam_step_bg")
-        else:
-            check(L.gsb_adam_step_ex(len(chunk), arr, flags.data_ptr(), skip_ptr, sd, _lib.stream_ptr()), "gsb_adam_step")
+        check(L.gsb_adam_step_ex(len(chunk), arr, flags.data_ptr(), skip_ptr,
+                                 None if step_sizes_dev is None else step_sizes_dev.data_ptr(), _lib.stream_ptr()),
+              "gsb_adam_step")
 
 
 def _validated_multiplier(param: torch.Tensor, mult):

@@ -31,7 +31,6 @@ from .per_point_adam import launch_adam
 from .scenes import Scene
 
 SEGMENTS = (("xyz", 3), ("f_dc", 3), ("f_rest", 45), ("opacity", 1), ("scaling", 3), ("rotation", 4))
-SH_NAMES = ("f_dc", "f_rest")     # read only by the colour pass (and its backward): the overlap mode's side stream
 
 
 def get_expon_lr_func(lr_init, lr_final, lr_delay_steps=0, lr_delay_mult=1.0, max_steps=1000000):
@@ -81,10 +80,8 @@ def _align(n, a=64):
 class JointTrainer:
     def __init__(self, scene: Scene, device, gt_images: Optional[torch.Tensor] = None,
                  cfg: Optional[OptimConfig] = None, world_size: int = 1, rank: int = 0,
-                 process_group=None, exchange: str = "allreduce", use_graph: bool = False, overlap: bool = False):
+                 process_group=None, exchange: str = "allreduce", use_graph: bool = False):
         self.cfg = cfg or OptimConfig()
-        self._side = None             # second stream of the overlap mode (see _overlap_iteration)
-        self._side_pending = False
         self.dev = torch.device(device)
         self.world_size, self.rank, self.pg = world_size, rank, process_group
         if exchange not in ("allreduce", "fused_p2p", "fused_p2p_nccl"):
@@ -180,23 +177,10 @@ class JointTrainer:
         # "fused_p2p" exchange is capturable (its collectives are this library's own kernels over peer memory; every
         # rank replays its own graph and the flag barriers inside keep the ranks in step).
         self.use_graph = bool(use_graph) and (world_size == 1 or self.exchange == "fused_p2p")
-        # overlap mode (single GPU, graph replay): the colour pass and the Adam update of the SH tensors (81 % of the
-        # parameter bytes; HBM-bound) run on a second stream beside the geometry pass, tile scan, scatter and tile sort
-        # (latency-bound) of the NEXT iteration -- see _overlap_iteration
-        self.overlap = bool(overlap) and self.use_graph and world_size == 1
-        self.overlap_ctas = 148 * 2   # persistent grid of the side-stream Adam: 512 threads per SM
-        if self.overlap:
-            self._side = torch.cuda.Stream(device=self.dev)
-            self._ev_step = torch.cuda.Event()
-            self._ev_color = torch.cuda.Event()
-            self._ev_end = torch.cuda.Event()
-            self._skip_latch = torch.zeros(1, dtype=torch.int32, device=self.dev)
-            self._flags_sh = torch.zeros(8, dtype=torch.int32, device=self.dev)
         self._graphs = {}
         self._after_backward = None   # test hook: called (and captured) between the backward and the optimizer step
-        # [0:7] step sizes in SEGMENTS order + pose; [8:13] the same for the non-SH subset (overlap mode's main launch)
-        self._step_host = torch.zeros(16, dtype=torch.float32).pin_memory()
-        self._step_dev = torch.zeros(16, dtype=torch.float32, device=self.dev)
+        self._step_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._step_dev = torch.zeros(8, dtype=torch.float32, device=self.dev)
         self._status_t.zero_()        # the forward serial number lives in these words
         self._fwd_count = 0
         self._polling = False
@@ -238,7 +222,7 @@ class JointTrainer:
     def _gauss(self, view: int) -> GsbGaussians:
         g = GsbGaussians()
         g.P, g.sh_packed, g.raw_params = self.P, 0, 1
-        p = self._params
+        p = self.params
         g.means3D = self.view(p, "xyz").data_ptr()
         g.scales = self.view(p, "scaling").data_ptr()
         g.rotations = self.view(p, "rotation").data_ptr()
@@ -247,20 +231,6 @@ class JointTrainer:
         g.sh_rest = self.view(p, "f_rest").data_ptr()
         g.pose = self.poses[view].data_ptr()
         return g
-
-    # The flat parameter / moment buffers.  In overlap mode the SH tensors' Adam update of the last step may still be
-    # running on the side stream when step() returns; reading the buffers through these attributes first makes the
-    # current stream wait for it (a stream-side wait, the host does not block).  The iteration itself uses the
-    # underscore names.
-    def join(self) -> None:
-        if self._side_pending:
-            torch.cuda.current_stream().wait_stream(self._side)
-            self._side_pending = False
-
-    params = property(lambda self: (self.join(), self._params)[1], lambda self, v: setattr(self, "_params", v))
-    exp_avg = property(lambda self: (self.join(), self._exp_avg)[1], lambda self, v: setattr(self, "_exp_avg", v))
-    exp_avg_sq = property(lambda self: (self.join(), self._exp_avg_sq)[1],
-                          lambda self, v: setattr(self, "_exp_avg_sq", v))
 
     # ------------------------------------------------------------------------------------------
     def _size_binning(self, R: int) -> None:
@@ -272,7 +242,6 @@ class JointTrainer:
     def _launch_forward(self, view: int) -> None:
         """Enqueue the forward without ever waiting for the GPU: the instance count R stays on the device; the
         host only provides a capacity (sized from the counts seen so far, +50 %) and reads R back lazily."""
-        self.join()
         L = _lib.lib()
         st = _lib.stream_ptr()
         cam, g = self._cam(), self._gauss(view)
@@ -374,46 +343,32 @@ class JointTrainer:
         ss = self._step_sizes()
         for i, v in enumerate(ss):
             self._step_host[i] = v
-        small = [v for (name, _), v in zip(SEGMENTS, ss) if name not in SH_NAMES] + ss[len(SEGMENTS):]
-        for i, v in enumerate(small):
-            self._step_host[8 + i] = v
         self._step_dev.copy_(self._step_host, non_blocking=True)
 
-    def optimizer_step(self, grad_scale: Optional[float] = None, _advance: bool = True, _dev_steps: bool = False,
-                       _subset: Optional[str] = None) -> None:
+    def optimizer_step(self, grad_scale: Optional[float] = None, _advance: bool = True, _dev_steps: bool = False) -> None:
         """PerPointAdam.step over the 6 Gaussian tensors + the pose table in one launch
-        (param groups and LRs of /root/reference/scene/gaussian_model.py:203-243).
-        _subset (overlap mode): "geom" = everything but the SH tensors (+ pose), on the current stream, gated on the
-        latched overflow word; "sh" = f_dc and f_rest from a small persistent grid (side stream), step sizes by value."""
+        (param groups and LRs of /root/reference/scene/gaussian_model.py:203-243)."""
         c = self.cfg
         if _advance:
             self.opt_step += 1
         t = self.opt_step
         b1, b2, eps = 0.9, 0.999, 1e-15
         corr = (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
-        lrs = self._lrs()
+        lrs = dict(xyz=self.xyz_sched(self.iteration), f_dc=c.feature_lr * 10, f_rest=c.feature_lr / 20.0 * 10,
+                   opacity=c.opacity_lr, scaling=c.scaling_lr * 10, rotation=c.rotation_lr * 10)
         gs = 1.0 / self.world_size if grad_scale is None else grad_scale
         entries = []
         for name, k in SEGMENTS:
-            if (_subset == "geom" and name in SH_NAMES) or (_subset == "sh" and name not in SH_NAMES):
-                continue
-            entries.append(dict(param=self.view(self._params, name), grad=self.view(self.grads, name),
-                                exp_avg=self.view(self._exp_avg, name), exp_avg_sq=self.view(self._exp_avg_sq, name),
+            entries.append(dict(param=self.view(self.params, name), grad=self.view(self.grads, name),
+                                exp_avg=self.view(self.exp_avg, name), exp_avg_sq=self.view(self.exp_avg_sq, name),
                                 per_point_lr=self.per_point_lr if name == "xyz" else None, row_len=k,
                                 step_size=lrs[name] * corr, beta1=b1, beta2=b2, eps=eps, weight_decay=0.0,
                                 grad_scale=gs))
-        if c.optim_pose and _subset != "sh":
+        if c.optim_pose:
             entries.append(dict(param=self.poses, grad=self.pose_grad, exp_avg=self.pose_m, exp_avg_sq=self.pose_v,
                                 per_point_lr=None, row_len=7, step_size=self.cam_sched(self.iteration) * corr,
                                 beta1=b1, beta2=b2, eps=eps, weight_decay=0.0, grad_scale=gs))
-        if _subset == "sh":
-            launch_adam(entries, self._flags_sh, skip_ptr=self._skip_latch.data_ptr(), max_ctas=self.overlap_ctas)
-        elif _subset == "geom":
-            launch_adam(entries, self.flags, skip_ptr=self._skip_latch.data_ptr(),
-                        step_sizes_dev=self._step_dev[8:] if _dev_steps else None)
-        else:
-            launch_adam(entries, self.flags, skip_ptr=self._skip_ptr(),
-                        step_sizes_dev=self._step_dev if _dev_steps else None)
+        launch_adam(entries, self.flags, skip_ptr=self._skip_ptr(), step_sizes_dev=self._step_dev if _dev_steps else None)
 
     def _skip_ptr(self):
         """Device word that makes the optimizer kernels skip the update: the forward's overflow status
@@ -500,97 +455,8 @@ class JointTrainer:
         else:
             dist.all_reduce(self._sync, group=self.pg)
 
-    def _launch_geom_binning(self, view: int) -> None:
-        """First half of the forward without the colour pass: geometry, tile scan, scatter, tile sort."""
-        L = _lib.lib()
-        st = _lib.stream_ptr()
-        cam, g = self._cam(), self._gauss(view)
-        check(L.gsb_preprocess_geom(ctypes.byref(cam), ctypes.byref(g), self.geom.data_ptr(), self.geom_bytes,
-                                    self.radii.data_ptr(), self.host_status[0].data_ptr(), st), "gsb_preprocess_geom")
-        check(L.gsb_binning(ctypes.byref(cam), self.P, self.geom.data_ptr(), self.binning.data_ptr(), self.bin_bytes,
-                            self.cap, st), "gsb_binning")
-        self._keep = (cam, g)
-
-    def _launch_color(self, view: int) -> None:
-        cam, g = self._cam(), self._gauss(view)
-        check(_lib.lib().gsb_preprocess_color(ctypes.byref(cam), ctypes.byref(g), self.geom.data_ptr(), self.geom_bytes,
-                                              _lib.stream_ptr()), "gsb_preprocess_color")
-
-    def _launch_blend(self) -> None:
-        cam, _ = self._keep
-        check(_lib.lib().gsb_blend_forward(ctypes.byref(cam), self.P, self.geom.data_ptr(), self.binning.data_ptr(),
-                                           self.bin_bytes, self.cap, self.image_buf.data_ptr(), self.color.data_ptr(),
-                                           self.host_status[1].data_ptr(), _lib.stream_ptr()), "gsb_blend_forward")
-
-    def _overlap_iteration(self, view: int, gt: torch.Tensor, do_opt: bool) -> None:
-        """One iteration in overlap mode.  Two streams:
-
-            main:  [graph A: geometry -> tile scan -> scatter -> tile sort]   wait(colour)   [graph B: blend -> loss ->
-                   backward -> Adam of xyz / opacity / scaling / rotation / pose]
-            side:  wait(previous main work) -> colour pass (SH -> RGB)  ...  wait(graph B) -> Adam of f_dc / f_rest
-
-        so the SH tensors' update of step s (HBM-bound, 76 % of the optimizer bytes) and the colour pass of step s+1 run
-        beside graph A of step s+1 (latency-bound kernels that never touch an SH tensor).  Nothing the side stream
-        writes is read by graph A; graph B starts only after the colour pass; the side-stream Adam reads the overflow
-        word through a latch written in graph B (the tile scan of the next step clears the original).  Step sizes of
-        the side launch travel by value (it is not part of a graph)."""
-        cur = torch.cuda.current_stream()
-        side = self._side
-        if do_opt:
-            self.opt_step += 1
-            self._upload_step_sizes()
-        for _attempt in range(2):
-            key = (view, gt.data_ptr(), do_opt, self.active_sh_degree, self.cap, self.exact_cull, "ov")
-            gs = self._graphs.get(key)
-            if gs is None:
-                if len(self._graphs) > 64:
-                    self._graphs.clear()
-                torch.cuda.synchronize()
-                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                with torch.cuda.graph(ga):
-                    self._launch_geom_binning(view)
-                with torch.cuda.graph(gb):
-                    self._launch_blend()
-                    self.loss_and_backward(view, gt)
-                    if self._after_backward is not None:
-                        self._after_backward()
-                    self._skip_latch.copy_(self._status_t[1:2])
-                    if do_opt:
-                        self.optimizer_step(_advance=False, _dev_steps=True, _subset="geom")
-                gs = self._graphs[key] = (ga, gb)
-            self._fwd_count += 1
-            self._polling = True
-            tl = getattr(self, "_timeline", None)        # diagnostics: timestamps of the five phase boundaries
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if tl is not None else None
-            self._ev_step.record(cur)
-            if ev: ev[0].record(cur)
-            with torch.cuda.stream(side):
-                side.wait_event(self._ev_step)          # the pose row / the records' previous readers (last backward)
-                self._launch_color(view)
-                self._ev_color.record(side)
-                if ev: ev[1].record(side)
-            gs[0].replay()
-            if ev: ev[2].record(cur)
-            cur.wait_event(self._ev_color)
-            gs[1].replay()
-            if ev: ev[3].record(cur)
-            if do_opt:
-                self._ev_end.record(cur)
-                with torch.cuda.stream(side):
-                    side.wait_event(self._ev_end)
-                    if ev: ev[4].record(side)
-                    self.optimizer_step(_advance=False, _subset="sh")
-                    if ev: ev[5].record(side)
-            if ev: tl.append(ev)
-            self._side_pending = True
-            if self._settle():
-                return
-        raise _lib.GsbError("graph replay: binning capacity exceeded twice in a row")
-
     def _graph_iteration(self, view: int, gt: torch.Tensor, do_opt: bool) -> None:
         """Replay (capturing on first use) the CUDA graph of one iteration on `view`."""
-        if self.overlap:
-            return self._overlap_iteration(view, gt, do_opt)
         if do_opt:
             self.opt_step += 1
             self._upload_step_sizes()                    # stream-ordered before the replay

@@ -13,6 +13,7 @@
 //   k_blend_fwd / k_blend_bwd     v1: one pixel per lane, 8 warps per tile, cooperative staging -- the first
 //                                 correct version, kept as the in-library cross-check (gsb_set_option)
 #include "gs_internal.cuh"
+#include "gs_tma.cuh"
 
 using namespace gsb;
 
@@ -329,39 +330,6 @@ constexpr int kThreads2 = 128;
 // byte count and issues cp.async.bulk.shared.global for the three slab arrays of the NEXT chunk
 // while the CTA blends the current one (double buffered).  SASS: UBLKCP + SYNCS.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0u;
-}
-// Bounded: a bulk copy that never lands must surface as a CUDA error (trap), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
-    if (spin > (1u << 24)) __trap();
-}
-
 struct SlabStage {
   float4 s0[kChunk], s1[kChunk], s2[kChunk];     // record rows 0..2 of the chunk's entries: x,y,A',B' | C',o,qthr',id | r,g,b,-
 };

@@ -18,6 +18,7 @@
 
 #include "gs_internal.cuh"
 #include "gs_tiles.cuh"
+#include "gs_tma.cuh"
 
 using namespace gsb;
 
@@ -249,56 +250,11 @@ __device__ __forceinline__ ShRows sh_rows(int sh_packed, int M) {
   return r;
 }
 
-// Full-CTA fast path (aligned pointers, split SH layout with 16 coefficients): all 128-bit global loads of
-// every array are issued before the first shared store, so each thread has ~15 independent 16-byte loads in
-// flight (memory-level parallelism instead of a load->store loop).
-template <int NF4, int MAXIT>
-__device__ __forceinline__ void ld_batch(float4 (&r)[MAXIT], const float* __restrict__ src) {
-  const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll
-  for (int i = 0; i < MAXIT; ++i) {
-    const int k = threadIdx.x + i * kPT;
-    if (k < NF4) r[i] = __ldg(s4 + k);
-  }
-}
-template <int NF4, int MAXIT>
-__device__ __forceinline__ void st_batch(const float4 (&r)[MAXIT], float* sm) {
-  float4* d4 = reinterpret_cast<float4*>(sm);
-#pragma unroll
-  for (int i = 0; i < MAXIT; ++i) {
-    const int k = threadIdx.x + i * kPT;
-    if (k < NF4) d4[k] = r[i];
-  }
-}
-
-__device__ __forceinline__ void load_block_inputs_full(const InPtrs& in, int first, bool use_sh, int D, float* sm) {
-  constexpr int N3 = 3 * kPT / 4, N4 = kPT, N1 = kPT / 4, NR = 45 * kPT / 4;
-  float4 rx[1], rs[1], rq[1], ro[1], rd[1], rr[(NR + kPT - 1) / kPT];
-  ld_batch<N3, 1>(rx, in.means + (size_t)3 * first);
-  ld_batch<N3, 1>(rs, in.scales + (size_t)3 * first);
-  ld_batch<N4, 1>(rq, in.rots + (size_t)4 * first);
-  ld_batch<N1, 1>(ro, in.opac + first);
-  if (use_sh) {
-    ld_batch<N3, 1>(rd, in.sh_dc + (size_t)3 * first);
-    if (D > 0) ld_batch<NR, (NR + kPT - 1) / kPT>(rr, in.sh_rest + (size_t)45 * first);
-  }
-  st_batch<N3, 1>(rx, sm + kSmXyz);
-  st_batch<N3, 1>(rs, sm + kSmSc);
-  st_batch<N4, 1>(rq, sm + kSmQ);
-  st_batch<N1, 1>(ro, sm + kSmOp);
-  if (use_sh) {
-    st_batch<N3, 1>(rd, sm + kSmSh);
-    if (D > 0) st_batch<NR, (NR + kPT - 1) / kPT>(rr, sm + kSmSh + 3 * kPT);
-  }
-}
-
+// Generic staging (ragged last CTA, unaligned pointers, packed SH layout, precomputed inputs); full aligned CTAs take
+// the bulk-copy path below.
 __device__ __forceinline__ void load_block_inputs(const InPtrs& in, int first, int nv, bool use_sh, int D, int M,
                                                   float* sm) {
   const bool vec = in.vec_ok != 0;
-  if (vec && nv == kPT && in.scales && in.rots && (!use_sh || (!in.sh_packed && M == 16))) {
-    load_block_inputs_full(in, first, use_sh, D, sm);
-    return;
-  }
   copy_in(sm + kSmXyz, in.means + (size_t)3 * first, 3 * nv, vec);
   if (in.scales) copy_in(sm + kSmSc, in.scales + (size_t)3 * first, 3 * nv, vec);
   if (in.rots) copy_in(sm + kSmQ, in.rots + (size_t)4 * first, 4 * nv, vec);
@@ -311,6 +267,37 @@ __device__ __forceinline__ void load_block_inputs(const InPtrs& in, int first, i
       if (D > 0 && M > 1)
         copy_in(sm + kSmSh + 3 * kPT, in.sh_rest + (size_t)3 * (M - 1) * first, 3 * (M - 1) * nv, vec);
     }
+  }
+}
+
+// The same full-CTA fast path with the copies done by the TMA unit: one thread arms an mbarrier with the byte count and
+// issues one bulk copy per input array (cp.async.bulk.shared.global, SASS UBLKCP); nothing passes through registers or
+// allocates L1 lines (with register staging, the 180 KB a resident set of CTAs keeps in flight is bounded by the L1
+// carve-out: giving shared memory the whole unified storage made both per-Gaussian kernels 8-13 % slower).
+__device__ __forceinline__ bool block_inputs_bulk_ok(const InPtrs& in, int nv, bool use_sh, int M) {
+  return in.vec_ok != 0 && nv == kPT && in.scales && in.rots && (!use_sh || (!in.sh_packed && M == 16));
+}
+__device__ __forceinline__ void bulk_load_block_inputs(const InPtrs& in, int first, bool use_sh, int D, float* sm,
+                                                       uint64_t* bar) {
+  constexpr uint32_t B3 = 3 * kPT * 4, B4 = 4 * kPT * 4, B1 = kPT * 4, BR = 45 * kPT * 4;
+  const bool rest = use_sh && D > 0;
+  mbar_expect_tx(bar, 2 * B3 + B4 + B1 + (use_sh ? B3 : 0u) + (rest ? BR : 0u));
+  bulk_g2s(sm + kSmXyz, in.means + (size_t)3 * first, B3, bar);
+  bulk_g2s(sm + kSmSc, in.scales + (size_t)3 * first, B3, bar);
+  bulk_g2s(sm + kSmQ, in.rots + (size_t)4 * first, B4, bar);
+  bulk_g2s(sm + kSmOp, in.opac + first, B1, bar);
+  if (use_sh) bulk_g2s(sm + kSmSh, in.sh_dc + (size_t)3 * first, B3, bar);
+  if (rest) bulk_g2s(sm + kSmSh + 3 * kPT, in.sh_rest + (size_t)45 * first, BR, bar);
+}
+// all threads call; returns when the CTA's inputs are in shared memory
+__device__ __forceinline__ void stage_block_inputs(const InPtrs& in, int first, int nv, bool use_sh, int D, int M, float* sm,
+                                                   uint64_t* bar) {
+  if (block_inputs_bulk_ok(in, nv, use_sh, M)) {
+    if (threadIdx.x == 0) bulk_load_block_inputs(in, first, use_sh, D, sm, bar);
+    mbar_wait(bar, 0u);
+  } else {
+    load_block_inputs(in, first, nv, use_sh, D, M, sm);
+    __syncthreads();
   }
 }
 
@@ -340,12 +327,13 @@ k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
     uint32_t* d = reinterpret_cast<uint32_t*>(cam);
     for (int k = threadIdx.x; k < (int)(sizeof(CamConst) / 4); k += blockDim.x) d[k] = s[k];
   }
+  __shared__ __align__(8) uint64_t s_bar;
+  if (threadIdx.x == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
   int first = blockIdx.x * kPT;
   int nv = min(kPT, in.P - first);
   bool use_sh = in.colors == nullptr;
   __syncthreads();
-  load_block_inputs(in, first, nv, use_sh, cam->D, cam->M, sm);
-  __syncthreads();
+  stage_block_inputs(in, first, nv, use_sh, cam->D, cam->M, sm, &s_bar);
   const int t = threadIdx.x;
   const bool active = t < nv;
   const int i = first + (active ? t : 0);
@@ -429,9 +417,13 @@ k_preprocess(InPtrs in, GeomView gv, int* __restrict__ radii) {
     gv.clamped[i] = (uint8_t)p.clamped;
     radii[i] = p.radius;
   }
+  tma_store_fence();                                 // the records leave as ONE bulk store (shared -> global, 48 nv bytes)
   __syncthreads();
-  float4* dst4 = gv.rec + 3 * (size_t)first;
-  for (int k = threadIdx.x; k < 3 * nv; k += kPT) dst4[k] = sm4[k];
+  if (threadIdx.x == 0) {
+    bulk_s2g(gv.rec + 3 * (size_t)first, sm4, (uint32_t)(48 * nv));
+    bulk_commit();
+    bulk_wait_read();
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -442,7 +434,10 @@ struct OutPtrs {
   float* dsh_dc; float* dsh_rest; float* dcolors; float* dcov3D;
 };
 
-__global__ void __launch_bounds__(kPT, 4)
+#ifndef GSB_PBWD_MINB
+#define GSB_PBWD_MINB 4
+#endif
+__global__ void __launch_bounds__(kPT, GSB_PBWD_MINB)
 k_preprocess_bwd(InPtrs in, GeomView gv, const int pose_only_layout, OutPtrs out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CamConst* cam = reinterpret_cast<CamConst*>(smem_raw);
@@ -453,14 +448,15 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int pose_only_layout, OutPtrs out
     uint32_t* d = reinterpret_cast<uint32_t*>(cam);
     for (int k = threadIdx.x; k < (int)(sizeof(CamConst) / 4); k += blockDim.x) d[k] = s[k];
   }
+  __shared__ __align__(8) uint64_t s_bar;
+  if (threadIdx.x == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
   const int first = blockIdx.x * kPT;
   const int nv = min(kPT, in.P - first);
   const bool use_sh = in.colors == nullptr;
   const bool vec = in.vec_ok != 0;
   __syncthreads();
   const int D = cam->D, M = cam->M;
-  load_block_inputs(in, first, nv, use_sh, D, M, sm);
-  __syncthreads();
+  stage_block_inputs(in, first, nv, use_sh, D, M, sm, &s_bar);
   const int t = threadIdx.x;
   const int i = first + t;
   float pa[16];
@@ -532,7 +528,25 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int pose_only_layout, OutPtrs out
       for (int k = 0; k < 6; ++k) out.dcov3D[6 * (size_t)i + k] = gg.dcov3D[k];
     }
   }
+  // Full CTA, aligned, split SH layout: every gradient array of the CTA leaves as one bulk store (shared -> global)
+  // issued by one thread; the generic path below covers ragged / unaligned / packed cases.
+  const bool bulk_out = vec && nv == kPT && !in.sh_packed && M == 16;
+  if (bulk_out) tma_store_fence();
   __syncthreads();
+  if (bulk_out) {
+    if (threadIdx.x == 0) {
+      constexpr uint32_t B3 = 3 * kPT * 4, B4 = 4 * kPT * 4, B1 = kPT * 4, BR = 45 * kPT * 4;
+      if (out.dmeans) bulk_s2g(out.dmeans + (size_t)3 * first, sm + kSmXyz, B3);
+      if (out.dscales) bulk_s2g(out.dscales + (size_t)3 * first, sm + kSmSc, B3);
+      if (out.drots) bulk_s2g(out.drots + (size_t)4 * first, sm + kSmQ, B4);
+      if (out.dopac) bulk_s2g(out.dopac + first, sm + kSmOp, B1);
+      if (use_sh && out.dsh_dc) {
+        bulk_s2g(out.dsh_dc + (size_t)3 * first, sm + kSmSh, B3);
+        if (out.dsh_rest) bulk_s2g(out.dsh_rest + (size_t)45 * first, sm + kSmSh + 3 * kPT, BR);
+      }
+      bulk_commit();
+    }
+  } else {
   if (out.dmeans) copy_out(out.dmeans + (size_t)3 * first, sm + kSmXyz, 3 * nv, vec);
   if (out.dscales) copy_out(out.dscales + (size_t)3 * first, sm + kSmSc, 3 * nv, vec);
   if (out.drots) copy_out(out.drots + (size_t)4 * first, sm + kSmQ, 4 * nv, vec);
@@ -545,6 +559,7 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int pose_only_layout, OutPtrs out
       if (M > 1 && out.dsh_rest)
         copy_out(out.dsh_rest + (size_t)3 * (M - 1) * first, sm + kSmSh + 3 * kPT, 3 * (M - 1) * nv, vec);
     }
+  }
   }
   // pose-gradient partials: warp shuffle, then across the 8 warps
   if (cam->pose_on) {
@@ -564,6 +579,7 @@ k_preprocess_bwd(InPtrs in, GeomView gv, const int pose_only_layout, OutPtrs out
       gv.pose_part[(size_t)blockIdx.x * 16 + threadIdx.x] = v;
     }
   }
+  if (bulk_out && threadIdx.x == 0) bulk_wait_read();   // shared memory must outlive the bulk stores reading it
 }
 
 // Pose-gradient partials [nblocks][16] -> 16 column sums (one CTA per column, deterministic order) ...

@@ -365,6 +365,46 @@ GS_HD bool rect_may_contribute(float x, float y, float A, float B, float C, floa
   return !(qmin > qthr);       // NaN -> keep
 }
 
+// The same predicate for a whole tile ROW at once.  The kept tiles of a row are those whose pixel-centre span
+// [16 tx, 16 tx + 15] meets the x-extent of (ellipse q <= qthr) intersected with the row's band of pixel centres -- in
+// exact arithmetic precisely the tiles for which the minimum of q over the tile's rectangle of pixel centres is <= qthr
+// (the ellipse cut by the band is convex, so its x-projection is an interval).  The extent of the cut is the ellipse's
+// own extreme point (dx = +-hx at dy = -+B hx / C) when that lies inside the band, else the outer root of
+// q(dx, dy_end) = qthr at one of the band's two ends: two square roots per row instead of one rectangle test per tile.
+// The interval is widened by kRowEps pixels: a false positive only costs a list entry (the blend applies the exact
+// per-pair rule), a false negative would lose a contribution.  ok == false (degenerate conic): use the per-tile test.
+constexpr float kRowEps = 0.02f;
+struct RowCull { float x, y, B, det, aq, invA, hx, hy, dyR; bool ok; };
+GS_HD RowCull row_cull_setup(float x, float y, float A, float B, float C, float qthr) {
+  RowCull r;
+  r.x = x; r.y = y; r.B = B;
+  r.det = A * C - B * B;
+  r.ok = (r.det > 0.f) && (A > 0.f) && (C > 0.f) && (qthr >= 0.f);
+  const float rdet = 1.0f / r.det;
+  r.hx = sqrtf(qthr * C * rdet);
+  r.hy = sqrtf(qthr * A * rdet) + kRowEps;
+  r.dyR = -B * r.hx / C;                                  // dy of the rightmost point (the leftmost one is at -dyR)
+  r.invA = 1.0f / A;
+  r.aq = A * qthr;
+  return r;
+}
+// tiles [ta, tb] of row ty (clipped to [rx0, rx1)) are kept; returns false when the row keeps nothing
+GS_HD bool row_keep_range(const RowCull& r, int ty, int H, int rx0, int rx1, int& ta, int& tb) {
+  const float y0 = (float)(ty * kBlock), y1 = fminf(y0 + (float)(kBlock - 1), (float)(H - 1));
+  const float lo = fmaxf(y0 - r.y, -r.hy), hi = fminf(y1 - r.y, r.hy);
+  if (lo > hi) return false;                              // the band misses the ellipse
+  const float slo = sqrtf(fmaxf(0.f, r.aq - r.det * lo * lo)), shi = sqrtf(fmaxf(0.f, r.aq - r.det * hi * hi));
+  const float blo = -r.B * lo, bhi = -r.B * hi;
+  const float xr = (r.dyR >= lo && r.dyR <= hi) ? r.hx : fmaxf(blo + slo, bhi + shi) * r.invA;
+  const float xl = (-r.dyR >= lo && -r.dyR <= hi) ? -r.hx : fminf(blo - slo, bhi - shi) * r.invA;
+  const float XL = r.x + xl - kRowEps, XR = r.x + xr + kRowEps;
+  // tile tx meets [XL, XR]  <=>  16 tx <= XR  and  16 tx + 15 >= XL
+  const float fa = ceilf((XL - (float)(kBlock - 1)) * (1.0f / kBlock)), fb = floorf(XR * (1.0f / kBlock));
+  ta = fa > (float)rx0 ? (int)fminf(fa, 1.0e6f) : rx0;
+  tb = fb < (float)(rx1 - 1) ? (int)fmaxf(fb, -1.0e6f) : rx1 - 1;
+  return tb >= ta;
+}
+
 // ------------------------------------------------------------------------------------------
 // Per-Gaussian backward (Appendix A.3).  dsplat = accumulated over pixels:
 //   [0,1] dL/d(pixel x,y)   [2,3,4] dL/dA, dL/dB (full), dL/dC   [5] dL/dopacity(activated)

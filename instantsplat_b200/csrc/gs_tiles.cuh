@@ -55,25 +55,33 @@ __device__ __forceinline__ bool tile_kept(const SplatRect& p, int tx, int ty, in
 
 // Small rects (area <= kCoopTiles <= 32): bit k of the keep mask = tile (ry0 + k / w, rx0 + k % w) survives the cull.
 // Computed once by k_preprocess and stored, so the emit pass replays exactly the tiles that were counted.
-__device__ __forceinline__ uint32_t rect_keep_mask(const SplatRect& p, int W, int H, bool cull) {
-  uint32_t m = 0u, bit = 1u;
-  for (int ty = p.ry0; ty < p.ry1; ++ty)
-    for (int tx = p.rx0; tx < p.rx1; ++tx) {
-      if (tile_kept(p, tx, ty, W, H, cull)) m |= bit;
-      bit <<= 1;
-    }
-  return m;
-}
-
 // Same walk, also counting every kept tile into tcount (RED.ADD, no return value).
-__device__ __forceinline__ uint32_t rect_keep_mask_count(const SplatRect& p, int W, int H, int gx, bool cull,
-                                                         uint32_t* tcount) {
+__device__ __forceinline__ uint32_t rect_keep_mask_count_tiles(const SplatRect& p, int W, int H, int gx, bool cull,
+                                                               uint32_t* tcount) {
   uint32_t m = 0u, bit = 1u;
   for (int ty = p.ry0; ty < p.ry1; ++ty)
     for (int tx = p.rx0; tx < p.rx1; ++tx) {
       if (tile_kept(p, tx, ty, W, H, cull)) { m |= bit; atomicAdd(tcount + (uint32_t)(ty * gx + tx), 1u); }
       bit <<= 1;
     }
+  return m;
+}
+
+// The same mask computed per tile ROW (gs_math.cuh row_keep_range: two square roots per row instead of one rectangle
+// test per tile); degenerate conics and cull-off fall back to the per-tile walk.
+__device__ __forceinline__ uint32_t rect_keep_mask_count(const SplatRect& p, int W, int H, int gx, bool cull,
+                                                         uint32_t* tcount) {
+  const RowCull rc = row_cull_setup(p.x, p.y, p.A, p.B, p.C, p.qthr);
+  if (!cull || !rc.ok) return rect_keep_mask_count_tiles(p, W, H, gx, cull, tcount);
+  const int w = p.rx1 - p.rx0;
+  uint32_t m = 0u;
+  for (int ty = p.ry0; ty < p.ry1; ++ty) {
+    int ta, tb;
+    if (!row_keep_range(rc, ty, H, p.rx0, p.rx1, ta, tb)) continue;
+    const int n = tb - ta + 1;                            // <= 24: the caller's rect has at most kCoopTiles tiles
+    m |= ((1u << n) - 1u) << ((ty - p.ry0) * w + (ta - p.rx0));
+    for (int tx = ta; tx <= tb; ++tx) atomicAdd(tcount + (uint32_t)(ty * gx + tx), 1u);
+  }
   return m;
 }
 

@@ -102,4 +102,19 @@ int host_rect_may_contribute(float x, float y, float A, float B, float C, float 
                              float ry0, float rx1, float ry1) {
   return rect_may_contribute(x, y, A, B, C, cull_threshold(opacity), rx0, ry0, rx1, ry1) ? 1 : 0;
 }
+
+// Row form of the same predicate (row_keep_range): kept[(ty - ry0) * (rx1 - rx0) + (tx - rx0)] = 1 for the kept tiles
+// of the tile rect [rx0, rx1) x [ry0, ry1) on an image of height H.  Returns 0 if the conic is degenerate.
+int host_row_keep(float x, float y, float A, float B, float C, float opacity, int H, int rx0, int ry0, int rx1, int ry1,
+                  int* kept) {
+  const RowCull rc = row_cull_setup(x, y, A, B, C, cull_threshold(opacity));
+  for (int k = 0; k < (rx1 - rx0) * (ry1 - ry0); ++k) kept[k] = 0;
+  if (!rc.ok) return 0;
+  for (int ty = ry0; ty < ry1; ++ty) {
+    int ta, tb;
+    if (!row_keep_range(rc, ty, H, rx0, rx1, ta, tb)) continue;
+    for (int tx = ta; tx <= tb; ++tx) kept[(ty - ry0) * (rx1 - rx0) + (tx - rx0)] = 1;
+  }
+  return 1;
+}
 }

@@ -139,3 +139,57 @@ def test_cull_predicate_is_conservative(lib):
             assert keep == 1
         n_rej += (keep == 0)
     assert n_rej > 500          # the predicate does cull
+
+
+def test_row_cull_is_conservative_and_agrees_with_the_tile_predicate(lib):
+    """row_keep_range (one interval per tile row; what k_preprocess uses for rects of <= 24 tiles) against (a) brute
+    force over the pixels -- a tile holding a pixel with alpha >= 1/255 must be kept -- and (b) the per-tile predicate
+    rect_may_contribute, which is the same set in exact arithmetic (disagreements only on borderline tiles)."""
+    rng = np.random.default_rng(1)
+    lib.host_rect_may_contribute.argtypes = [ctypes.c_float] * 10
+    lib.host_row_keep.argtypes = [ctypes.c_float] * 6 + [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_int)]
+    W, H = 30 * 16 - 5, 20 * 16 - 9              # last tile row / column are partial
+    gx, gy = 30, 20
+    n_tiles = n_kept = n_diff = n_must = 0
+    for it in range(3000):
+        s1, s2 = rng.uniform(0.3, 30), rng.uniform(0.3, 30)
+        if it % 5 == 0:
+            s2 = s1 * rng.uniform(0.02, 0.2)             # needle-shaped
+        th = rng.uniform(0, math.pi)
+        a = (math.cos(th) * s1) ** 2 + (math.sin(th) * s2) ** 2 + 0.3
+        c = (math.sin(th) * s1) ** 2 + (math.cos(th) * s2) ** 2 + 0.3
+        b = math.cos(th) * math.sin(th) * (s1 * s1 - s2 * s2)
+        det = a * c - b * b
+        A, B, C = c / det, -b / det, a / det
+        op = rng.uniform(0.004, 1.0) if it % 7 else rng.uniform(0.0, 0.006)
+        x, y = rng.uniform(-30, W + 30), rng.uniform(-30, H + 30)
+        rad = math.ceil(3 * math.sqrt(0.5 * (a + c) + math.sqrt(max(0.1, (0.5 * (a + c)) ** 2 - det))))
+        rx0, rx1 = min(gx, max(0, int((x - rad) / 16))), min(gx, max(0, int((x + rad + 15) / 16)))
+        ry0, ry1 = min(gy, max(0, int((y - rad) / 16))), min(gy, max(0, int((y + rad + 15) / 16)))
+        w, h = rx1 - rx0, ry1 - ry0
+        if w * h == 0:
+            continue
+        kept = (ctypes.c_int * (w * h))()
+        ok = lib.host_row_keep(x, y, A, B, C, op, H, rx0, ry0, rx1, ry1, kept)
+        if not ok:
+            assert op * 255 < 0.999          # only "can never reach 1/255" is allowed to be degenerate here
+            continue
+        for ty in range(ry0, ry1):
+            for tx in range(rx0, rx1):
+                x0, y0 = tx * 16, ty * 16
+                x1, y1 = min(x0 + 15, W - 1), min(y0 + 15, H - 1)
+                xs, ys = np.meshgrid(np.arange(x0, x1 + 1), np.arange(y0, y1 + 1))
+                dx, dy = x - xs, y - ys
+                power = -0.5 * (A * dx * dx + C * dy * dy) - B * dx * dy
+                must = bool(((power <= 0) & (op * np.exp(power) >= 1 / 255)).any())
+                k = kept[(ty - ry0) * w + (tx - rx0)]
+                if must:
+                    assert k == 1, (it, tx, ty, x, y, A, B, C, op)
+                t = lib.host_rect_may_contribute(x, y, A, B, C, op, x0, y0, x1, y1)
+                n_tiles += 1
+                n_kept += k
+                n_must += must
+                n_diff += int(k != t)
+    assert n_tiles > 20000 and n_must > 3000
+    assert n_kept < 0.9 * n_tiles                 # it does cull
+    assert n_diff <= 0.003 * n_tiles, (n_diff, n_tiles)

@@ -85,40 +85,56 @@ __device__ __forceinline__ uint32_t rect_keep_mask_count(const SplatRect& p, int
   return m;
 }
 
-// Warp-synchronous delivery of every lane's kept tiles (all 32 lanes must call).  Each round every lane offers
-// its next kept tile; lanes offering the SAME tile are merged with match.any so that one atomic per distinct
-// tile is issued (neighbouring Gaussians overlap the same tiles, which otherwise serialises in the L2 atomic
-// unit).  Emit mode: the group leader reserves cnt slots with one atomicAdd and every member takes base + rank.
+// Warp-synchronous EMISSION of every lane's kept tiles (all 32 lanes must call).  Each round every lane offers its
+// next TWO kept tiles; lanes offering the SAME tile in the same slot are merged with match.any so that one atomic per
+// distinct tile is issued (neighbouring Gaussians overlap the same tiles, which otherwise serialises in the L2 atomic
+// unit): the group leader reserves cnt slots with one atomicAdd and every member takes base + rank.  Both slots'
+// atomics are issued before either result is consumed -- the kernel is a chain of atomic round trips per warp, two
+// in flight halve it.
 __device__ __forceinline__ void warp_sink_masks(uint32_t mask, int rx0, int ry0, int w, int gx, const TileSink& s,
                                                 unsigned long long key) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const uint32_t inv_w = w > 0 ? (65536u + (uint32_t)w - 1u) / (uint32_t)w : 0u;   // k / w for k < 32, w <= 32
+  const uint32_t below = (1u << lane) - 1u;
   while (__any_sync(full, mask != 0u)) {
-    const bool has = mask != 0u;
-    uint32_t tile = 0xFFFFFFFFu;
-    if (has) {
-      const uint32_t k = (uint32_t)__ffs(mask) - 1u;
-      mask &= mask - 1u;
-      const uint32_t ky = (k * inv_w) >> 16;
-      tile = (uint32_t)(ry0 + (int)ky) * (uint32_t)gx + (uint32_t)(rx0 + (int)(k - ky * (uint32_t)w));
+    bool has[2];
+    uint32_t tile[2], base[2], cnt[2];
+    unsigned grp[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      has[u] = mask != 0u;
+      tile[u] = 0xFFFFFFFFu;
+      if (has[u]) {
+        const uint32_t k = (uint32_t)__ffs(mask) - 1u;
+        mask &= mask - 1u;
+        const uint32_t ky = (k * inv_w) >> 16;
+        tile[u] = (uint32_t)(ry0 + (int)ky) * (uint32_t)gx + (uint32_t)(rx0 + (int)(k - ky * (uint32_t)w));
+      }
+      grp[u] = __match_any_sync(full, tile[u]);
+      cnt[u] = (uint32_t)__popc(grp[u]);
     }
-    const unsigned grp = __match_any_sync(full, tile);
-    const int leader = __ffs(grp) - 1;
-    const uint32_t cnt = (uint32_t)__popc(grp);
-    if (s.pairs) {
-      uint32_t base = 0u;
-      if (has && lane == leader) base = atomicAdd(s.tcursor + tile, cnt);
-      base = __shfl_sync(full, base, leader);
-      if (has) {
-        const uint32_t pos = base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
-        if (pos < s.tcount[tile]) {
-          const uint32_t dst = s.tstart[tile] + pos;
+    uint32_t tc[2], ts[2];                               // loaded before the atomics (which the compiler must not reorder)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      tc[u] = has[u] ? s.tcount[tile[u]] : 0u;
+      ts[u] = has[u] ? s.tstart[tile[u]] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      base[u] = 0u;
+      if (has[u] && lane == __ffs(grp[u]) - 1) base[u] = atomicAdd(s.tcursor + tile[u], cnt[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      base[u] = __shfl_sync(full, base[u], __ffs(grp[u]) - 1);
+      if (has[u]) {
+        const uint32_t pos = base[u] + (uint32_t)__popc(grp[u] & below);
+        if (pos < tc[u]) {
+          const uint32_t dst = ts[u] + pos;
           if (dst < s.cap) s.pairs[dst] = key;
         }
       }
-    } else if (has && lane == leader) {
-      atomicAdd(s.tcount + tile, cnt);
     }
   }
 }

@@ -114,12 +114,15 @@ def measured_peaks():
 # ----------------------------------------------------------------------------------------------
 def cpu_sample_plan(sc, n_steps):
     """What one CPU step computes -- a pure function of the workload and of the number of steps (no wall-clock
-    probing, so two runs sample the same work).  Budget: about 12 s of CPU work per step when there are few steps
-    (default bench: 1 warm-up + 3 timed), shrinking as 1/steps so that `--impl reference --steps K` stays within a few
-    minutes."""
+    probing, so two runs sample the same work).  About 12 s of CPU work per step (all Gaussians, 128 stratified tiles,
+    the full frame's loss) for up to 32 steps -- the default bench's cpu_baseline (1 warm-up + 3 timed) and the driver's
+    `--impl reference --steps 20 --warmup 5` (about 5 minutes) -- and a sample shrinking to no less than 1/8 of that for
+    longer runs.  Smaller samples are NOT used: PyTorch's per-operator overhead dominates small tensors and the
+    extrapolation then under-reports the CPU (full sample 0.0069 it/s, 1/7 sample 0.0031, 1/51 sample 0.0010:
+    profiles/r02_bench_reference_*.json)."""
     gx, gy = (sc.width + 15) // 16, (sc.height + 15) // 16
     T = gx * gy
-    shrink = max(1, (n_steps + 3) // 4)
+    shrink = 1 if n_steps <= 32 else min(8, (n_steps + 31) // 32)
     n_g = max(2_000, min(sc.P, sc.P // shrink))                      # Gaussians projected (fwd+bwd) and Adam-updated
     n_t = max(4, min(T, 128 // shrink))                              # tiles blended (fwd+bwd), stratified over the frame
     rows = max(32, min(sc.height, sc.height // shrink))              # image rows of the L1+SSIM loss (fwd+bwd)

@@ -195,24 +195,14 @@ GS_HD void sh_to_rgb_bwd(int D, const float* sh_rest, float x, float y, float z,
   ddir[0] = gx; ddir[1] = gy; ddir[2] = gz;
 }
 
-// The mean handed to the rasterizer: the fused InstantSplat pose pre-transform R m + t (or m itself).  Explicit fma
-// chain, so that every kernel that needs the transformed mean obtains the same bits.
-GS_HD void pose_mean(const CamConst& c, const float* m, float* mc) {
-  if (c.pose_on) {
-    mc[0] = fmaf(c.Rc[0], m[0], fmaf(c.Rc[1], m[1], fmaf(c.Rc[2], m[2], c.tc[0])));
-    mc[1] = fmaf(c.Rc[3], m[0], fmaf(c.Rc[4], m[1], fmaf(c.Rc[5], m[2], c.tc[1])));
-    mc[2] = fmaf(c.Rc[6], m[0], fmaf(c.Rc[7], m[1], fmaf(c.Rc[8], m[2], c.tc[2])));
-  } else {
-    mc[0] = m[0]; mc[1] = m[1]; mc[2] = m[2];
-  }
-}
-
 // Geometry part of the forward (Appendix A.2 steps 1-7).  cov3D_pre: 6 floats or nullptr.
 GS_HD void project_geometry(const CamConst& c, const GaussIn& in, const float* cov3D_pre, Proj& o) {
   o.visible = 0; o.radius = 0; o.rx0 = o.ry0 = o.rx1 = o.ry1 = 0; o.clamped = 0;
   // ---- fused pose pre-transform + activations
-  pose_mean(c, in.m, o.mc);
   if (c.pose_on) {
+    o.mc[0] = c.Rc[0] * in.m[0] + c.Rc[1] * in.m[1] + c.Rc[2] * in.m[2] + c.tc[0];
+    o.mc[1] = c.Rc[3] * in.m[0] + c.Rc[4] * in.m[1] + c.Rc[5] * in.m[2] + c.tc[1];
+    o.mc[2] = c.Rc[6] * in.m[0] + c.Rc[7] * in.m[1] + c.Rc[8] * in.m[2] + c.tc[2];
     float w1 = c.qc[0], x1 = c.qc[1], y1 = c.qc[2], z1 = c.qc[3];
     float w2 = in.q[0], x2 = in.q[1], y2 = in.q[2], z2 = in.q[3];
     o.q[0] = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2;
@@ -220,6 +210,7 @@ GS_HD void project_geometry(const CamConst& c, const GaussIn& in, const float* c
     o.q[2] = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2;
     o.q[3] = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
   } else {
+    o.mc[0] = in.m[0]; o.mc[1] = in.m[1]; o.mc[2] = in.m[2];
     o.q[0] = in.q[0]; o.q[1] = in.q[1]; o.q[2] = in.q[2]; o.q[3] = in.q[3];
   }
   if (c.raw_params) {

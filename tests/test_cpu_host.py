@@ -148,6 +148,24 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
 
 
+def test_cpu_sample_plan_is_a_pure_function_and_never_tiny():
+    """The CPU arm's per-step sample depends on the workload and the step count only (two runs time the same work), is
+    the FULL sample for the runs the driver makes (<= 32 steps) and never shrinks below 1/8 of it."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    import types
+    sc = types.SimpleNamespace(P=1_000_000, width=1920, height=1080)
+    full = bench.cpu_sample_plan(sc, 4)
+    assert full == bench.cpu_sample_plan(sc, 4)
+    assert full["n_gauss"] == sc.P and len(full["tiles"]) == 128 and full["rows"] == sc.height
+    assert bench.cpu_sample_plan(sc, 25) == full                      # --steps 20 --warmup 5
+    big = bench.cpu_sample_plan(sc, 1000)
+    assert big["n_gauss"] * 8 >= sc.P and len(big["tiles"]) * 8 >= 128 and big["rows"] * 8 >= sc.height
+    assert len(set(full["tiles"])) == 128 and max(full["tiles"]) < full["T"]
+
+
 def test_debug_mode_writes_snapshot_of_failing_call(tmp_path, monkeypatch):
     """Upstream's Python wrapper dumps the arguments of a failing forward to snapshot_fw.dump in debug mode and
     re-raises (boundary B2 error behaviour)."""
